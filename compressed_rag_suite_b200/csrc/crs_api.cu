@@ -1,0 +1,616 @@
+// C ABI of libcrs.so (include/crs.h): index object, memory, dispatch.
+//
+// The index keeps the stored rows of ONE shard contiguous in HBM
+// ([count][row_bytes], row_bytes a multiple of 128) plus per-search scratch.
+// All kernels are enqueued on the index's stream; nothing here computes on the CPU
+// except parameter plumbing (thresholds, plans).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "crs_internal.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? CRS_ENOMEM : CRS_ECUDA;
+}
+#define CRS_CUDA(call)                                   \
+    do {                                                 \
+        cudaError_t _e = (call);                         \
+        if (_e != cudaSuccess) return cuda_fail(_e, #call); \
+    } while (0)
+
+bool is_device_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+const int kFloatNch[] = {1, 2, 3, 4, 6, 8, 12, 16};
+const int kIntNch[] = {1, 2, 3, 4, 6, 8};
+
+// rows are zero-padded to one of the row widths the scan kernels are instantiated for
+int padded_dim_for(int dim, crs_dtype store) {
+    const int unit = (store == CRS_F16 || store == CRS_BF16) ? 64 : (store == CRS_I8 ? 128 : 1024);
+    const int* tab = (store == CRS_F16 || store == CRS_BF16) ? kFloatNch : kIntNch;
+    const int n = (store == CRS_F16 || store == CRS_BF16) ? 8 : 6;
+    for (int i = 0; i < n; ++i)
+        if (tab[i] * unit >= dim) return tab[i] * unit;
+    return -1;
+}
+size_t row_bytes_for(int dim_padded, crs_dtype store) {
+    switch (store) {
+        case CRS_F16: case CRS_BF16: return (size_t)dim_padded * 2;
+        case CRS_I8: return (size_t)dim_padded;
+        default: return (size_t)dim_padded / 8;
+    }
+}
+
+template <typename T>
+struct DevScratch {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct crs_index {
+    int dim = 0, dim_padded = 0;
+    crs_dtype store = CRS_F16;
+    crs_metric metric = CRS_COSINE;
+    int device = 0;
+    uint32_t row_base = 0;
+    size_t row_bytes = 0;
+    int64_t count = 0, capacity = 0, reserve_hint = 0;
+    uint8_t* codes = nullptr;
+    float i8_scale = 1.0f;
+    float row_norm_bound = 1.00390625f;
+    cudaStream_t stream = nullptr;
+    int num_sms = 0;
+    // options
+    int force_path = -1;
+    int force_exact = 0;
+    double eps_scale = 1.0;
+    // scratch
+    DevScratch<float> qsrc, qnorms, norms_tmp;
+    DevScratch<uint8_t> qcodes, stage_rows;
+    DevScratch<uint64_t> cand;
+    DevScratch<int32_t> flags, counts_dev;
+    DevScratch<uint32_t> ids_dev;
+    DevScratch<uint8_t> scores_dev;
+    int32_t* n_flagged = nullptr;      // device counters: [0] this search, [1] since create
+    crs_search_stats stats{};
+    std::mutex mu;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int grow(crs_index* ix, int64_t need) {
+    if (need <= ix->capacity) return CRS_OK;
+    int64_t cap = std::max<int64_t>(need, ix->capacity + ix->capacity / 2);
+    cap = std::max<int64_t>(cap, ix->reserve_hint);
+    cap = std::max<int64_t>(cap, 1024);
+    uint8_t* p = nullptr;
+    CRS_CUDA(cudaMalloc(&p, (size_t)cap * ix->row_bytes));
+    if (ix->count > 0)
+        CRS_CUDA(cudaMemcpyAsync(p, ix->codes, (size_t)ix->count * ix->row_bytes, cudaMemcpyDeviceToDevice, ix->stream));
+    if (ix->codes) { CRS_CUDA(cudaStreamSynchronize(ix->stream)); cudaFree(ix->codes); }
+    ix->codes = p;
+    ix->capacity = cap;
+    return CRS_OK;
+}
+
+// smallest int raw score whose float similarity passes fl32(sim) >= fl32(min_similarity)
+int32_t min_raw_for(const crs_index* ix, float min_similarity) {
+    if (!(min_similarity > -INFINITY)) return INT32_MIN;
+    if (isnan(min_similarity)) return INT32_MAX;
+    auto sim = [&](int64_t raw) -> float {
+        if (ix->store == CRS_I8) {
+            const float s2 = (float)(((double)ix->i8_scale / 127.0) * ((double)ix->i8_scale / 127.0));
+            return (float)(int32_t)raw * s2;
+        }
+        return (float)((double)raw / (double)ix->dim);
+    };
+    const int64_t lo = (ix->store == CRS_I8) ? -(int64_t)ix->dim_padded * 127 * 127 : -(int64_t)ix->dim;
+    const int64_t hi = -lo;
+    if (sim(hi) < min_similarity) return INT32_MAX;
+    int64_t a = lo, b = hi;                 // sim is monotone non-decreasing in raw: binary search
+    while (a < b) {
+        const int64_t m = a + (b - a) / 2;
+        if (sim(m) >= min_similarity) b = m; else a = m + 1;
+    }
+    return (int32_t)a;
+}
+
+__global__ void fill_pad_kernel(uint32_t* ids, void* scores, int32_t* counts, int nq, int k, int is_int) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq * k) {
+        ids[i] = CRS_PAD_ID;
+        if (is_int) reinterpret_cast<int32_t*>(scores)[i] = INT32_MIN;
+        else reinterpret_cast<float*>(scores)[i] = -INFINITY;
+    }
+    if (i < nq) counts[i] = 0;
+}
+__global__ void set_flags_kernel(int32_t* flags, int nq, int v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq) flags[i] = v;
+}
+
+}  // namespace
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+const char* crs_last_error(void) { return g_last_error.c_str(); }
+int crs_version(void) { return 100; }
+
+int crs_index_create(crs_index** out, int dim, crs_dtype store, crs_metric metric,
+                     int device, uint32_t row_base, int64_t reserve_rows) {
+    if (!out) return fail(CRS_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (dim <= 0) return fail(CRS_EINVAL, "dim must be positive");
+    if (store != CRS_F16 && store != CRS_BF16 && store != CRS_I8 && store != CRS_B1)
+        return fail(CRS_EINVAL, "store dtype must be F16, BF16, I8 or B1");
+    if (metric != CRS_COSINE && metric != CRS_IP) return fail(CRS_EINVAL, "metric must be COSINE or IP");
+    const int dp = padded_dim_for(dim, store);
+    if (dp < 0) return fail(CRS_EINVAL, "dim too large for this store dtype");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(CRS_ECUDA, "no CUDA device: libcrs has no CPU implementation");
+    }
+    if (device < 0 || device >= ndev) return fail(CRS_EINVAL, "device ordinal out of range");
+    cudaDeviceProp prop;
+    CRS_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(CRS_ECUDA, "libcrs kernels are built for sm_100a only");
+    DeviceGuard g(device);
+    crs_index* ix = new crs_index();
+    ix->dim = dim; ix->dim_padded = dp; ix->store = store; ix->metric = metric;
+    ix->device = device; ix->row_base = row_base;
+    ix->row_bytes = row_bytes_for(dp, store);
+    ix->reserve_hint = reserve_rows;
+    ix->num_sms = prop.multiProcessorCount;
+    e = cudaMalloc(&ix->n_flagged, 2 * sizeof(int32_t));
+    if (e != cudaSuccess) { delete ix; return cuda_fail(e, "cudaMalloc"); }
+    cudaMemset(ix->n_flagged, 0, 2 * sizeof(int32_t));
+    if (reserve_rows > 0) {
+        int rc = grow(ix, reserve_rows);
+        if (rc != CRS_OK) { cudaFree(ix->n_flagged); delete ix; return rc; }
+    }
+    *out = ix;
+    return CRS_OK;
+}
+
+int crs_index_destroy(crs_index* ix) {
+    if (!ix) return CRS_OK;
+    {
+        DeviceGuard g(ix->device);
+        cudaStreamSynchronize(ix->stream);
+        if (ix->codes) cudaFree(ix->codes);
+        if (ix->n_flagged) cudaFree(ix->n_flagged);
+        ix->qsrc.release(); ix->qnorms.release(); ix->norms_tmp.release(); ix->qcodes.release();
+        ix->stage_rows.release(); ix->cand.release(); ix->flags.release(); ix->counts_dev.release();
+        ix->ids_dev.release(); ix->scores_dev.release();
+    }
+    delete ix;
+    return CRS_OK;
+}
+
+int crs_index_set_stream(crs_index* ix, void* cuda_stream) {
+    if (!ix) return fail(CRS_EINVAL, "index is NULL");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    ix->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    return CRS_OK;
+}
+
+int crs_index_set_option(crs_index* ix, const char* name, int64_t value) {
+    if (!ix || !name) return fail(CRS_EINVAL, "bad argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    if (!strcmp(name, "force_path")) ix->force_path = (int)value;
+    else if (!strcmp(name, "force_exact")) ix->force_exact = (int)value;
+    else if (!strcmp(name, "eps_scale")) ix->eps_scale = (double)value / 1000.0;
+    else return fail(CRS_EINVAL, std::string("unknown option ") + name);
+    return CRS_OK;
+}
+
+int crs_index_add(crs_index* ix, const void* rows, int64_t n, crs_dtype src_dtype) {
+    if (!ix) return fail(CRS_EINVAL, "index is NULL");
+    if (n < 0) return fail(CRS_EINVAL, "n must be >= 0");
+    if (n == 0) return CRS_OK;
+    if (!rows) return fail(CRS_EINVAL, "rows is NULL");
+    if (src_dtype != CRS_F32) return fail(CRS_EINVAL, "rows must be float32");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    if ((uint64_t)ix->row_base + (uint64_t)ix->count + (uint64_t)n >= 0xFFFFFFFFull)
+        return fail(CRS_EINVAL, "row ids would overflow uint32");
+    int rc = grow(ix, ix->count + n);
+    if (rc != CRS_OK) return rc;
+    const bool dev = is_device_ptr(rows);
+    const int64_t chunk = dev ? n : std::min<int64_t>(n, 1 << 16);
+    if (!dev) CRS_CUDA(ix->stage_rows.ensure((size_t)chunk * ix->dim * sizeof(float)));
+    if (ix->metric == CRS_IP && (ix->store == CRS_F16 || ix->store == CRS_BF16))
+        CRS_CUDA(ix->norms_tmp.ensure((size_t)chunk));
+    for (int64_t off = 0; off < n; off += chunk) {
+        const int64_t m = std::min(chunk, n - off);
+        const float* src = reinterpret_cast<const float*>(rows) + off * ix->dim;
+        if (!dev) {
+            CRS_CUDA(cudaMemcpyAsync(ix->stage_rows.p, src, (size_t)m * ix->dim * sizeof(float),
+                                     cudaMemcpyHostToDevice, ix->stream));
+            src = reinterpret_cast<const float*>(ix->stage_rows.p);
+        }
+        float* norms = (ix->metric == CRS_IP && ix->norms_tmp.p) ? ix->norms_tmp.p : nullptr;
+        CRS_CUDA(crs::launch_encode(ix->stream, src, m, ix->dim, ix->dim_padded, ix->store, ix->metric,
+                                    ix->i8_scale, ix->codes + (size_t)(ix->count + off) * ix->row_bytes, norms));
+        if (norms) {   // inner-product space: track the largest stored-row norm for the error bound
+            std::vector<float> h((size_t)m);
+            CRS_CUDA(cudaMemcpyAsync(h.data(), norms, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
+            CRS_CUDA(cudaStreamSynchronize(ix->stream));
+            for (float v : h) ix->row_norm_bound = std::max(ix->row_norm_bound, v);
+        } else if (!dev) {
+            CRS_CUDA(cudaStreamSynchronize(ix->stream));   // staging buffer is reused by the next chunk
+        }
+    }
+    ix->count += n;
+    return CRS_OK;
+}
+
+int crs_index_count(const crs_index* ix, int64_t* out_count) {
+    if (!ix || !out_count) return fail(CRS_EINVAL, "bad argument");
+    *out_count = ix->count;
+    return CRS_OK;
+}
+
+int crs_index_info(const crs_index* ix, int32_t* dim, int32_t* dim_padded, int64_t* row_bytes,
+                   int32_t* store, int32_t* metric) {
+    if (!ix) return fail(CRS_EINVAL, "index is NULL");
+    if (dim) *dim = ix->dim;
+    if (dim_padded) *dim_padded = ix->dim_padded;
+    if (row_bytes) *row_bytes = (int64_t)ix->row_bytes;
+    if (store) *store = (int32_t)ix->store;
+    if (metric) *metric = (int32_t)ix->metric;
+    return CRS_OK;
+}
+
+int crs_index_similarity_scale(const crs_index* ix, double* out_scale) {
+    if (!ix || !out_scale) return fail(CRS_EINVAL, "bad argument");
+    switch (ix->store) {
+        case CRS_I8: *out_scale = (double)(float)(((double)ix->i8_scale / 127.0) * ((double)ix->i8_scale / 127.0)); break;
+        case CRS_B1: *out_scale = 1.0 / (double)ix->dim; break;
+        default: *out_scale = 1.0;
+    }
+    return CRS_OK;
+}
+
+int crs_index_last_stats(const crs_index* ix, crs_search_stats* out) {
+    if (!ix || !out) return fail(CRS_EINVAL, "bad argument");
+    *out = ix->stats;
+    int32_t tot = 0;
+    DeviceGuard g(ix->device);
+    CRS_CUDA(cudaMemcpy(&tot, ix->n_flagged + 1, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    out->uncertified_total = tot;
+    return CRS_OK;
+}
+
+int crs_index_search(crs_index* ix, const void* queries, int nq, int k, float min_similarity,
+                     uint32_t* out_ids, void* out_scores, int32_t* out_counts) {
+    if (!ix) return fail(CRS_EINVAL, "index is NULL");
+    if (nq < 0 || k <= 0) return fail(CRS_EINVAL, "nq must be >= 0 and k > 0");
+    if (nq == 0) return CRS_OK;
+    if (!queries || !out_ids || !out_scores || !out_counts) return fail(CRS_EINVAL, "NULL buffer");
+    const bool is_float = ix->store == CRS_F16 || ix->store == CRS_BF16;
+    const bool is_int = !is_float;
+    // float stores need head-room above k for certification (finalize.cu)
+    int lpl;
+    if (is_float) { if (k <= 16) lpl = 1; else if (k <= 112) lpl = 4; else return fail(CRS_EINVAL, "k > 112 not supported for float stores"); }
+    else { if (k <= 32) lpl = 1; else if (k <= 128) lpl = 4; else return fail(CRS_EINVAL, "k > 128 not supported"); }
+    const int M = 32 * lpl;
+
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = ix->stream;
+    int launches = 0;
+
+    const bool q_dev = is_device_ptr(queries);
+    const bool ids_dev = is_device_ptr(out_ids), sc_dev = is_device_ptr(out_scores), cn_dev = is_device_ptr(out_counts);
+    if (!(ids_dev == sc_dev && sc_dev == cn_dev))
+        return fail(CRS_EINVAL, "out_ids/out_scores/out_counts must all be host or all be device buffers");
+    const bool out_dev = ids_dev;
+    const size_t nk = (size_t)nq * k;
+
+    uint32_t* d_ids = out_ids; void* d_scores = out_scores; int32_t* d_counts = out_counts;
+    if (!out_dev) {
+        CRS_CUDA(ix->ids_dev.ensure(nk));
+        CRS_CUDA(ix->scores_dev.ensure(nk * 4));
+        CRS_CUDA(ix->counts_dev.ensure((size_t)nq));
+        d_ids = ix->ids_dev.p; d_scores = ix->scores_dev.p; d_counts = ix->counts_dev.p;
+    }
+
+    bool copied = false;
+    auto copy_out = [&]() -> cudaError_t {
+        cudaError_t e = cudaMemcpyAsync(out_ids, d_ids, nk * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out_scores, d_scores, nk * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out_counts, d_counts, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+        return e;
+    };
+
+    if (ix->count == 0) {
+        fill_pad_kernel<<<(unsigned)((std::max(nk, (size_t)nq) + 255) / 256), 256, 0, st>>>(d_ids, d_scores, d_counts, nq, k, is_int);
+        CRS_CUDA(cudaGetLastError());
+        ++launches;
+    } else {
+        // ---- queries -> canonical stored codes
+        const float* qd = reinterpret_cast<const float*>(queries);
+        if (!q_dev) {
+            CRS_CUDA(ix->qsrc.ensure((size_t)nq * ix->dim));
+            CRS_CUDA(cudaMemcpyAsync(ix->qsrc.p, queries, (size_t)nq * ix->dim * sizeof(float), cudaMemcpyHostToDevice, st));
+            qd = ix->qsrc.p;
+        }
+        CRS_CUDA(ix->qcodes.ensure((size_t)nq * ix->row_bytes));
+        CRS_CUDA(ix->qnorms.ensure((size_t)nq));
+        CRS_CUDA(crs::launch_encode(st, qd, nq, ix->dim, ix->dim_padded, ix->store, ix->metric, ix->i8_scale,
+                                    ix->qcodes.p, ix->qnorms.p));
+        ++launches;
+
+        // ---- plan: persistent grid, one candidate list per CTA
+        crs::ScanPlan plan;
+        plan.lpl = lpl;
+        plan.grid = ix->num_sms;
+        const int n_lists = plan.grid;
+        CRS_CUDA(ix->cand.ensure((size_t)nq * n_lists * M));
+        CRS_CUDA(ix->flags.ensure((size_t)nq));
+
+        crs::FinalizeArgs fa{};
+        fa.cand = ix->cand.p; fa.n_lists = n_lists; fa.lpl = lpl; fa.nq = nq; fa.k = k;
+        fa.codes = ix->codes; fa.qcodes = ix->qcodes.p; fa.qnorms = ix->qnorms.p;
+        fa.dim_padded = ix->dim_padded; fa.bf16 = ix->store == CRS_BF16;
+        fa.row_norm_bound = ix->row_norm_bound;
+        fa.min_similarity = min_similarity; fa.row_base = ix->row_base;
+        fa.out_ids = d_ids; fa.out_scores = d_scores; fa.out_counts = d_counts;
+        fa.flags = ix->flags.p; fa.n_flagged = ix->n_flagged; fa.is_int = is_int;
+
+        ix->stats.path = 0; ix->stats.grid = plan.grid; ix->stats.list_len = M;
+        if (is_float) {
+            // error bound of the fp32 scan score (any summation order): Dp * 2^-24 * |q| * |c|
+            const float eps_rel = (float)((double)ix->dim_padded * ldexp(1.0, -24) * 1.01 * ix->eps_scale);
+            fa.eps_rel = eps_rel;
+            bool need_exact = ix->force_exact != 0;
+            if (!need_exact) {
+                // cosine queries are unit rows (|q| <= 1.0039); for ip the norm is only known on the
+                // device, so the pre-filter is left off and the threshold applied on the exact score.
+                float tau_pre = -INFINITY;
+                if (ix->metric == CRS_COSINE && min_similarity > -INFINITY)
+                    tau_pre = min_similarity - eps_rel * 1.00390625f * ix->row_norm_bound;
+                for (int q = 0; q < nq; ++q) {
+                    CRS_CUDA(crs::launch_scan_f16(st, ix->codes, ix->count, ix->dim_padded, fa.bf16,
+                                                  ix->qcodes.p + (size_t)q * ix->row_bytes, tau_pre,
+                                                  ix->cand.p + (size_t)q * n_lists * M, plan));
+                    ++launches;
+                }
+                fa.mode = 0; fa.only_flagged = 0;
+                CRS_CUDA(cudaMemsetAsync(ix->n_flagged, 0, sizeof(int32_t), st));
+                CRS_CUDA(crs::launch_finalize(st, fa));
+                ++launches;
+                if (out_dev) {
+                    need_exact = true;          // cannot look at the flags without a sync: enqueue the conditional pass
+                } else {
+                    int32_t nf = 0;             // results and the flag count come back in one sync
+                    CRS_CUDA(copy_out());
+                    CRS_CUDA(cudaMemcpyAsync(&nf, ix->n_flagged, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+                    CRS_CUDA(cudaStreamSynchronize(st));
+                    need_exact = nf > 0;
+                    copied = !need_exact;
+                }
+            } else {
+                set_flags_kernel<<<(nq + 255) / 256, 256, 0, st>>>(ix->flags.p, nq, 1);
+                CRS_CUDA(cudaGetLastError());
+                ++launches;
+            }
+            if (need_exact) {
+                CRS_CUDA(crs::launch_exact_scan(st, ix->codes, ix->count, ix->dim_padded, fa.bf16, ix->qcodes.p, nq,
+                                                ix->flags.p, min_similarity, ix->cand.p, plan));
+                fa.mode = 1; fa.only_flagged = 1;
+                CRS_CUDA(crs::launch_finalize(st, fa));
+                launches += 2;
+            }
+        } else {
+            const int32_t min_raw = min_raw_for(ix, min_similarity);
+            for (int q = 0; q < nq; ++q) {
+                const uint8_t* qc = ix->qcodes.p + (size_t)q * ix->row_bytes;
+                uint64_t* cd = ix->cand.p + (size_t)q * n_lists * M;
+                if (ix->store == CRS_I8)
+                    CRS_CUDA(crs::launch_scan_i8(st, ix->codes, ix->count, ix->dim_padded, qc, min_raw, cd, plan));
+                else
+                    CRS_CUDA(crs::launch_scan_b1(st, ix->codes, ix->count, ix->dim_padded, ix->dim, qc, min_raw, cd, plan));
+                ++launches;
+            }
+            fa.mode = 1; fa.only_flagged = 0;
+            CRS_CUDA(crs::launch_finalize(st, fa));
+            ++launches;
+        }
+    }
+
+    if (!out_dev && !copied) {
+        CRS_CUDA(copy_out());
+        CRS_CUDA(cudaStreamSynchronize(st));
+    }
+    ix->stats.kernel_launches = launches;
+    ix->stats.searches_total += nq;
+    return CRS_OK;
+}
+
+int crs_index_fetch_rows(crs_index* ix, const uint32_t* ids, int n, void* out_codes) {
+    if (!ix) return fail(CRS_EINVAL, "index is NULL");
+    if (n < 0) return fail(CRS_EINVAL, "n must be >= 0");
+    if (n == 0) return CRS_OK;
+    if (!ids || !out_codes) return fail(CRS_EINVAL, "NULL buffer");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = ix->stream;
+    const bool ids_dev = is_device_ptr(ids), out_dev = is_device_ptr(out_codes);
+    uint32_t* d_ids = nullptr; uint8_t* d_out = nullptr;
+    const uint32_t* ids_p = ids; void* out_p = out_codes;
+    const size_t bytes = (size_t)n * ix->row_bytes;
+    if (!ids_dev) {
+        CRS_CUDA(cudaMalloc(&d_ids, (size_t)n * sizeof(uint32_t)));
+        CRS_CUDA(cudaMemcpyAsync(d_ids, ids, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        ids_p = d_ids;
+    }
+    if (!out_dev) {
+        CRS_CUDA(cudaMalloc(&d_out, bytes));
+        CRS_CUDA(cudaMemcpyAsync(d_out, out_codes, bytes, cudaMemcpyHostToDevice, st));   // keep rows of other shards
+        out_p = d_out;
+    }
+    CRS_CUDA(crs::launch_gather_rows(st, ix->codes, ix->row_bytes, ix->count, ix->row_base, ids_p, n, out_p));
+    if (!out_dev) CRS_CUDA(cudaMemcpyAsync(out_codes, d_out, bytes, cudaMemcpyDeviceToHost, st));
+    if (!ids_dev || !out_dev) {
+        CRS_CUDA(cudaStreamSynchronize(st));
+        if (d_ids) cudaFree(d_ids);
+        if (d_out) cudaFree(d_out);
+    }
+    return CRS_OK;
+}
+
+int crs_mmr(crs_index* ix, const void* vecs, const double* relevance, int nq, int m, int k_out,
+            double lambda, int32_t* out_order) {
+    if (!ix) return fail(CRS_EINVAL, "index is NULL");
+    if (nq < 0 || m < 0 || k_out <= 0) return fail(CRS_EINVAL, "bad sizes");
+    if (nq == 0 || m == 0) return CRS_OK;
+    if (m > 128) return fail(CRS_EINVAL, "m > 128 candidates not supported");
+    if (!vecs || !relevance || !out_order) return fail(CRS_EINVAL, "NULL buffer");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = ix->stream;
+    const size_t vbytes = (size_t)nq * m * ix->row_bytes, rbytes = (size_t)nq * m * sizeof(double);
+    const size_t obytes = (size_t)nq * k_out * sizeof(int32_t);
+    void* d_v = nullptr; double* d_r = nullptr; int32_t* d_o = nullptr;
+    const void* v = vecs; const double* r = relevance; int32_t* o = out_order;
+    if (!is_device_ptr(vecs)) { CRS_CUDA(cudaMalloc(&d_v, vbytes)); CRS_CUDA(cudaMemcpyAsync(d_v, vecs, vbytes, cudaMemcpyHostToDevice, st)); v = d_v; }
+    if (!is_device_ptr(relevance)) { CRS_CUDA(cudaMalloc(&d_r, rbytes)); CRS_CUDA(cudaMemcpyAsync(d_r, relevance, rbytes, cudaMemcpyHostToDevice, st)); r = d_r; }
+    const bool o_dev = is_device_ptr(out_order);
+    if (!o_dev) { CRS_CUDA(cudaMalloc(&d_o, obytes)); o = d_o; }
+    CRS_CUDA(crs::launch_mmr(st, v, ix->store, ix->dim_padded, ix->dim, r, nq, m, k_out, lambda, o));
+    if (!o_dev) CRS_CUDA(cudaMemcpyAsync(out_order, d_o, obytes, cudaMemcpyDeviceToHost, st));
+    if (d_v || d_r || d_o) {
+        CRS_CUDA(cudaStreamSynchronize(st));
+        if (d_v) cudaFree(d_v);
+        if (d_r) cudaFree(d_r);
+        if (d_o) cudaFree(d_o);
+    }
+    return CRS_OK;
+}
+
+int crs_merge_topk(void* cuda_stream, const uint32_t* ids, const void* scores, int is_int,
+                   int n_lists, int nq, int k_in, int k_out,
+                   uint32_t* out_ids, void* out_scores, int32_t* out_counts) {
+    if (nq < 0 || n_lists <= 0 || k_in <= 0 || k_out <= 0 || k_out > k_in)
+        return fail(CRS_EINVAL, "bad sizes");
+    if (k_in > crs::kMaxListLen) return fail(CRS_EINVAL, "k_in > 128 not supported");
+    if (nq == 0) return CRS_OK;
+    if (!is_device_ptr(ids) || !is_device_ptr(scores) || !is_device_ptr(out_ids) || !is_device_ptr(out_scores) ||
+        !is_device_ptr(out_counts))
+        return fail(CRS_EINVAL, "crs_merge_topk takes device buffers");
+    CRS_CUDA(crs::launch_merge_topk(reinterpret_cast<cudaStream_t>(cuda_stream), ids, scores, is_int, n_lists, nq,
+                                    k_in, k_out, out_ids, out_scores, out_counts));
+    return CRS_OK;
+}
+
+// ---- persistence: 64-byte header + raw stored rows -------------------------------------
+struct CrsFileHeader {
+    char magic[8];          // "CRSIDX1\0"
+    int32_t dim, dim_padded, store, metric;
+    int64_t count;
+    float i8_scale, row_norm_bound;
+    uint8_t pad[24];
+};
+static_assert(sizeof(CrsFileHeader) == 64, "header is 64 bytes");
+
+int crs_index_save(crs_index* ix, const char* path) {
+    if (!ix || !path) return fail(CRS_EINVAL, "bad argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(CRS_EIO, std::string("cannot open ") + path);
+    CrsFileHeader h{};
+    memcpy(h.magic, "CRSIDX1", 8);
+    h.dim = ix->dim; h.dim_padded = ix->dim_padded; h.store = ix->store; h.metric = ix->metric;
+    h.count = ix->count; h.i8_scale = ix->i8_scale; h.row_norm_bound = ix->row_norm_bound;
+    bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
+    const size_t chunk_rows = std::max<size_t>(1, (64u << 20) / ix->row_bytes);
+    std::vector<uint8_t> buf(chunk_rows * ix->row_bytes);
+    for (int64_t off = 0; ok && off < ix->count; off += (int64_t)chunk_rows) {
+        const size_t m = (size_t)std::min<int64_t>((int64_t)chunk_rows, ix->count - off);
+        cudaError_t e = cudaMemcpyAsync(buf.data(), ix->codes + (size_t)off * ix->row_bytes, m * ix->row_bytes,
+                                        cudaMemcpyDeviceToHost, ix->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
+        if (e != cudaSuccess) { fclose(f); return cuda_fail(e, "cudaMemcpy"); }
+        ok = fwrite(buf.data(), ix->row_bytes, m, f) == m;
+    }
+    ok = (fclose(f) == 0) && ok;
+    return ok ? CRS_OK : fail(CRS_EIO, std::string("write failed: ") + path);
+}
+
+int crs_index_load(crs_index** out, const char* path, int device, uint32_t row_base) {
+    if (!out || !path) return fail(CRS_EINVAL, "bad argument");
+    *out = nullptr;
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(CRS_EIO, std::string("cannot open ") + path);
+    CrsFileHeader h{};
+    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "CRSIDX1", 8) != 0) {
+        fclose(f);
+        return fail(CRS_EIO, "not a CRS index file");
+    }
+    crs_index* ix = nullptr;
+    int rc = crs_index_create(&ix, h.dim, (crs_dtype)h.store, (crs_metric)h.metric, device, row_base, h.count);
+    if (rc != CRS_OK) { fclose(f); return rc; }
+    if (ix->dim_padded != h.dim_padded) { fclose(f); crs_index_destroy(ix); return fail(CRS_EIO, "layout mismatch"); }
+    ix->i8_scale = h.i8_scale; ix->row_norm_bound = h.row_norm_bound;
+    DeviceGuard g(device);
+    const size_t chunk_rows = std::max<size_t>(1, (64u << 20) / ix->row_bytes);
+    std::vector<uint8_t> buf(chunk_rows * ix->row_bytes);
+    for (int64_t off = 0; off < h.count; off += (int64_t)chunk_rows) {
+        const size_t m = (size_t)std::min<int64_t>((int64_t)chunk_rows, h.count - off);
+        if (fread(buf.data(), ix->row_bytes, m, f) != m) { fclose(f); crs_index_destroy(ix); return fail(CRS_EIO, "short read"); }
+        cudaError_t e = cudaMemcpy(ix->codes + (size_t)off * ix->row_bytes, buf.data(), m * ix->row_bytes, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { fclose(f); crs_index_destroy(ix); return cuda_fail(e, "cudaMemcpy"); }
+    }
+    fclose(f);
+    ix->count = h.count;
+    *out = ix;
+    return CRS_OK;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

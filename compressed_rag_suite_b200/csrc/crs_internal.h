@@ -1,0 +1,78 @@
+// Internal declarations shared by the translation units of libcrs.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/crs.h"
+
+namespace crs {
+
+// Widest candidate list a search keeps per query: M = 32 * LPL keys, LPL in {1, 4}.
+constexpr int kMaxListLen = 128;
+
+struct ScanPlan {
+    int grid;          // persistent CTAs
+    int lpl;           // list entries per lane (1 -> M = 32, 4 -> M = 128)
+};
+
+// K0: fp32 rows -> stored codes (normalise for cosine, cast / quantise / sign-pack).
+//   norms_out (optional, [n]): fp32 upper bound of the Euclidean norm of each STORED row.
+cudaError_t launch_encode(cudaStream_t st, const float* src, int64_t n, int dim, int dim_padded,
+                          crs_dtype store, crs_metric metric, float i8_scale, void* dst, float* norms_out);
+
+// K1: fp16 / bf16 stream scan of `n` stored rows against ONE stored query; writes one
+// sorted candidate list of M keys per CTA: cand[cta * M + i].
+cudaError_t launch_scan_f16(cudaStream_t st, const void* codes, int64_t n, int dim_padded, bool bf16,
+                            const void* qcodes, float tau_pre, uint64_t* cand, const ScanPlan& plan);
+// K2 / K3: exact integer scans (dp4a dot, xor+popcount); same candidate-list output.
+cudaError_t launch_scan_i8(cudaStream_t st, const void* codes, int64_t n, int dim_padded,
+                           const void* qcodes, int32_t min_raw, uint64_t* cand, const ScanPlan& plan);
+cudaError_t launch_scan_b1(cudaStream_t st, const void* codes, int64_t n, int dim_padded, int dim,
+                           const void* qcodes, int32_t min_raw, uint64_t* cand, const ScanPlan& plan);
+
+struct FinalizeArgs {
+    const uint64_t* cand;      // [nq][n_lists][M] sorted lists
+    int n_lists;
+    int lpl;
+    int nq;
+    int k;
+    int mode;                  // 0: float store, rescore + certify; 1: keys are already exact (ints or fallback)
+    int only_flagged;          // 1: process only queries with flags[q] != 0 (fallback pass), then clear the flag
+    const void* codes;         // stored corpus rows (mode 0)
+    const void* qcodes;        // [nq][dim_padded]
+    const float* qnorms;       // [nq]
+    int dim_padded;
+    int bf16;
+    float eps_rel;             // approx-score error bound = eps_rel * qnorm * row_norm_bound
+    float row_norm_bound;
+    float min_similarity;      // float-domain threshold on the exact score (mode 0 only)
+    uint32_t row_base;
+    uint32_t* out_ids;         // [nq][k]
+    void* out_scores;          // [nq][k] f32 or i32 raw
+    int32_t* out_counts;       // [nq]
+    int32_t* flags;            // [nq] 1 = not certified (mode 0 writes, only_flagged reads)
+    int32_t* n_flagged;        // device counter of uncertified queries (statistics)
+    int is_int;                // raw scores are int32
+};
+cudaError_t launch_finalize(cudaStream_t st, const FinalizeArgs& a);
+
+// Exact fallback for float stores: fp64-sequential score of every row for each flagged
+// query; one sorted list per CTA, keys carry the exact fl32 score.
+cudaError_t launch_exact_scan(cudaStream_t st, const void* codes, int64_t n, int dim_padded, bool bf16,
+                              const void* qcodes, int nq, const int32_t* flags, float min_similarity,
+                              uint64_t* cand, const ScanPlan& plan);
+
+// K7: merge G lists of k_in (id, raw score) per query into the global top k_out.
+cudaError_t launch_merge_topk(cudaStream_t st, const uint32_t* ids, const void* scores, int is_int,
+                              int n_lists, int nq, int k_in, int k_out,
+                              uint32_t* out_ids, void* out_scores, int32_t* out_counts);
+
+// K6: greedy MMR over m candidate vectors per query.
+cudaError_t launch_mmr(cudaStream_t st, const void* vecs, crs_dtype store, int dim_padded, int dim,
+                       const double* relevance, int nq, int m, int k_out, double lambda,
+                       int32_t* out_order);
+
+// gather stored rows by local row index
+cudaError_t launch_gather_rows(cudaStream_t st, const void* codes, size_t row_bytes, int64_t n_rows,
+                               uint32_t row_base, const uint32_t* ids, int n, void* out);
+
+}  // namespace crs

@@ -1,0 +1,238 @@
+// Finalize — per query: merge the per-CTA candidate lists, rescore exactly,
+// certify, apply the threshold and emit the top-k.  Plus the exact fp64 fallback
+// scan used when a float-store query cannot be certified.
+//
+// Why: the fast passes (K1 scan, K4 tcgen05 GEMM) rank rows on fp32-accumulated
+// scores whose summation order differs from any CPU brute force.  The canonical
+// result (oracle/search.py) is defined on fl32(fp64-sequential dot), so each query's
+// M best rows by fast score are rescored here in fp64, sequentially over
+// j = 0..Dp-1 (products of fp16/bf16 values are exact in fp64, so the value equals
+// the CPU's bit for bit), then re-ranked.  The result is *certified* when no row
+// outside the M candidates can reach the k-th exact score:
+//      list not full                          -> nothing was cut
+//      fast(M-th candidate) + eps < exact(k-th)   (or < threshold when count < k)
+// with eps = Dp * 2^-24 * |q| * max|c| * scale bounding the fast pass' error.
+// Otherwise flags[q] = 1 and the exact fallback (exact_scan + finalize mode 1)
+// recomputes that query exhaustively in fp64.  Integer stores (I8/B1) are exact
+// already and use mode 1 directly.
+#include "common.cuh"
+#include "crs_internal.h"
+
+namespace crs {
+
+constexpr int kFinalizeWarps = 16;
+
+template <bool BF16>
+__device__ __forceinline__ void unpack8(const uint4& v, double (&o)[8]) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if constexpr (BF16) {
+            o[2 * i] = (double)__uint_as_float(w[i] << 16);
+            o[2 * i + 1] = (double)__uint_as_float(w[i] & 0xFFFF0000u);
+        } else {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+            o[2 * i] = (double)f.x;
+            o[2 * i + 1] = (double)f.y;
+        }
+    }
+}
+
+// canonical score: sequential fp64 accumulation over j = 0..Dp-1, one rounding to fp32
+template <bool BF16>
+__device__ __forceinline__ float exact_dot(const uint4* __restrict__ row, const uint4* __restrict__ q, int chunks) {
+    double acc = 0.0;
+    for (int c = 0; c < chunks; ++c) {
+        double a[8], b[8];
+        unpack8<BF16>(row[c], a);
+        unpack8<BF16>(q[c], b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc = fma(a[j], b[j], acc);
+    }
+    return (float)acc;
+}
+
+template <int LPL>
+__global__ void __launch_bounds__(kFinalizeWarps * 32)
+finalize_kernel(FinalizeArgs a) {
+    constexpr int M = 32 * LPL;
+    __shared__ uint64_t stage[kFinalizeWarps * M];
+    __shared__ uint64_t fast_keys[M];
+    __shared__ uint64_t exact_keys[M];
+    const int q = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (a.only_flagged && a.flags[q] == 0) return;
+
+    // 1. merge the n_lists sorted lists of this query (warp w takes lists w, w+16, ...)
+    uint64_t e[LPL];
+#pragma unroll
+    for (int s = 0; s < LPL; ++s) e[s] = 0ull;
+    const uint64_t* base = a.cand + (size_t)q * a.n_lists * M;
+    for (int l = warp; l < a.n_lists; l += kFinalizeWarps) {
+        uint64_t b[LPL];
+#pragma unroll
+        for (int s = 0; s < LPL; ++s) b[s] = base[(size_t)l * M + lane * LPL + s];
+        warp_merge_desc<LPL>(e, b, lane);
+    }
+    block_merge_lists<LPL, kFinalizeWarps>(e, stage, warp, lane);
+    if (warp == 0) {
+#pragma unroll
+        for (int s = 0; s < LPL; ++s) fast_keys[lane * LPL + s] = e[s];
+    }
+    __syncthreads();
+
+    // 2. exact rescoring, one thread per candidate (float stores only)
+    if (a.mode == 0) {
+        if (threadIdx.x < M) {
+            const uint64_t fk = fast_keys[threadIdx.x];
+            uint64_t ek = 0ull;
+            if (fk != 0ull) {
+                const uint32_t id = key_id(fk);
+                const int chunks = a.dim_padded / 8;
+                const uint4* row = reinterpret_cast<const uint4*>(a.codes) + (size_t)id * chunks;
+                const uint4* qv = reinterpret_cast<const uint4*>(a.qcodes) + (size_t)q * chunks;
+                const float s = a.bf16 ? exact_dot<true>(row, qv, chunks) : exact_dot<false>(row, qv, chunks);
+                if (s >= a.min_similarity) ek = make_key(orderable_f32(s), id);
+            }
+            exact_keys[threadIdx.x] = ek;
+        }
+        __syncthreads();
+    }
+
+    // 3. warp 0: final order, certification, output
+    if (warp != 0) return;
+    uint64_t x[LPL];
+    const uint64_t* srck = (a.mode == 0) ? exact_keys : fast_keys;
+#pragma unroll
+    for (int s = 0; s < LPL; ++s) x[s] = srck[lane * LPL + s];
+    if (a.mode == 0) warp_sort_desc<LPL>(x, lane);
+
+    // number of valid keys (sorted desc, empties (0) at the end)
+    int nvalid = 0;
+#pragma unroll
+    for (int s = 0; s < LPL; ++s) nvalid += (x[s] != 0ull);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) nvalid += __shfl_xor_sync(CRS_FULL_MASK, nvalid, off);
+    const int count = min(nvalid, a.k);
+
+    if (a.mode == 0) {
+        const uint64_t last_fast = fast_keys[M - 1];          // M-th candidate by fast score (0 = list not full)
+        bool certified = true;
+        if (last_fast != 0ull) {
+            const float a_min = unorderable_f32(key_ord(last_fast));
+            const float eps = a.eps_rel * a.qnorms[q] * a.row_norm_bound;
+            float bound;
+            if (nvalid >= a.k) {
+                // k-th exact score: element k-1 of x
+                const int kk = a.k - 1;
+                uint64_t kth = 0ull;
+#pragma unroll
+                for (int s = 0; s < LPL; ++s) {
+                    const uint64_t v = shfl_u64(x[s], kk / LPL);
+                    if (s == kk % LPL) kth = v;
+                }
+                bound = unorderable_f32(key_ord(kth));
+            } else {
+                bound = a.min_similarity;                     // fewer than k pass: nothing cut may pass either
+            }
+            certified = (a_min + eps < bound);
+        }
+        if (lane == 0) {
+            a.flags[q] = certified ? 0 : 1;
+            if (!certified) { atomicAdd(a.n_flagged, 1); atomicAdd(a.n_flagged + 1, 1); }
+        }
+    } else if (a.only_flagged && lane == 0) {
+        a.flags[q] = 0;
+    }
+
+#pragma unroll
+    for (int s = 0; s < LPL; ++s) {
+        const int i = lane * LPL + s;
+        if (i < a.k) {
+            const bool ok = i < count;
+            const uint64_t key = x[s];
+            a.out_ids[(size_t)q * a.k + i] = ok ? key_id(key) + a.row_base : CRS_PAD_ID;
+            if (a.is_int) {
+                reinterpret_cast<int32_t*>(a.out_scores)[(size_t)q * a.k + i] =
+                    ok ? unorderable_i32(key_ord(key)) : INT32_MIN;
+            } else {
+                reinterpret_cast<float*>(a.out_scores)[(size_t)q * a.k + i] =
+                    ok ? unorderable_f32(key_ord(key)) : -INFINITY;
+            }
+        }
+    }
+    if (lane == 0) a.out_counts[q] = count;
+}
+
+cudaError_t launch_finalize(cudaStream_t st, const FinalizeArgs& a) {
+    if (a.nq <= 0) return cudaSuccess;
+    if (a.k > 32 * a.lpl) return cudaErrorInvalidValue;
+    if (a.lpl == 1) finalize_kernel<1><<<a.nq, kFinalizeWarps * 32, 0, st>>>(a);
+    else if (a.lpl == 4) finalize_kernel<4><<<a.nq, kFinalizeWarps * 32, 0, st>>>(a);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ exact fallback scan
+// Thread per row, fp64 sequential — slow by design (rows are walked uncoalesced), only
+// run for the rare queries finalize could not certify.  One sorted list per CTA and
+// flagged query, keys carry the exact fl32 score, so finalize mode 1 just merges.
+constexpr int kExactWarps = 8;
+
+template <int LPL, bool BF16>
+__global__ void __launch_bounds__(kExactWarps * 32)
+exact_scan_kernel(const uint4* __restrict__ codes, int64_t n_rows, int chunks, const uint4* __restrict__ qcodes,
+                  int nq, const int32_t* __restrict__ flags, float min_similarity, uint64_t* __restrict__ cand) {
+    constexpr int M = 32 * LPL;
+    __shared__ uint64_t stage[kExactWarps * M];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int q = 0; q < nq; ++q) {
+        if (flags[q] == 0) continue;               // uniform across the grid
+        WarpTopM<LPL> top; top.init();
+        const uint4* qv = qcodes + (size_t)q * chunks;
+        const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+        for (int64_t r0 = (int64_t)blockIdx.x * blockDim.x + warp * 32; r0 < n_rows; r0 += stride) {
+            const int64_t row = r0 + lane;
+            uint64_t key = 0ull;
+            if (row < n_rows) {
+                const float s = exact_dot<BF16>(codes + row * chunks, qv, chunks);
+                if (s >= min_similarity) key = make_key(orderable_f32(s), (uint32_t)row);
+            }
+            unsigned bal = __ballot_sync(CRS_FULL_MASK, key > top.floor_key);
+            while (bal) {
+                const int src = __ffs(bal) - 1;
+                bal &= bal - 1;
+                const uint64_t kb = shfl_u64(key, src);
+                if (kb > top.floor_key) top.insert(kb, lane);
+            }
+        }
+        warp_sort_desc<LPL>(top.e, lane);
+        block_merge_lists<LPL, kExactWarps>(top.e, stage, warp, lane);
+        if (warp == 0) {
+#pragma unroll
+            for (int s = 0; s < LPL; ++s)
+                cand[((size_t)q * gridDim.x + blockIdx.x) * M + lane * LPL + s] = top.e[s];
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_exact_scan(cudaStream_t st, const void* codes, int64_t n, int dim_padded, bool bf16,
+                              const void* qcodes, int nq, const int32_t* flags, float min_similarity,
+                              uint64_t* cand, const ScanPlan& plan) {
+    if (nq <= 0) return cudaSuccess;
+    const int chunks = dim_padded / 8;
+    const uint4* c = reinterpret_cast<const uint4*>(codes);
+    const uint4* qv = reinterpret_cast<const uint4*>(qcodes);
+    const int threads = kExactWarps * 32;
+    if (plan.lpl == 1) {
+        if (bf16) exact_scan_kernel<1, true><<<plan.grid, threads, 0, st>>>(c, n, chunks, qv, nq, flags, min_similarity, cand);
+        else      exact_scan_kernel<1, false><<<plan.grid, threads, 0, st>>>(c, n, chunks, qv, nq, flags, min_similarity, cand);
+    } else {
+        if (bf16) exact_scan_kernel<4, true><<<plan.grid, threads, 0, st>>>(c, n, chunks, qv, nq, flags, min_similarity, cand);
+        else      exact_scan_kernel<4, false><<<plan.grid, threads, 0, st>>>(c, n, chunks, qv, nq, flags, min_similarity, cand);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace crs

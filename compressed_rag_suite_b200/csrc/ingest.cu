@@ -1,0 +1,118 @@
+// K0 — ingest: fp32 rows -> stored codes.
+//
+// Replaces what Chroma does with `collection.add(embeddings=...)`
+// (reference rag/indexing.py:114-119; cosine space normalises, :83) and
+// additionally casts / quantises / sign-packs the rows into the HBM layout the
+// scan and GEMM kernels stream.  Arithmetic is the canonical definition in
+// oracle/encode.py: n2 accumulated sequentially in fp64, y = x / sqrt(n2) in fp64,
+// one rounding to the store dtype.  Bit-exact with the oracle by construction.
+//
+// Mapping: one warp owns 32 consecutive rows.  Row segments of 32 columns are
+// loaded coalesced (lane = column) into a padded smem tile and walked by
+// lane = row, so the fp64 accumulation order is j = 0..D-1 for every row.
+#include "common.cuh"
+#include "crs_internal.h"
+
+namespace crs {
+
+constexpr int kIngestWarps = 4;
+
+template <int STORE>   // crs_dtype value
+__global__ void __launch_bounds__(kIngestWarps * 32)
+encode_kernel(const float* __restrict__ src, int64_t n, int dim, int dim_padded, int cosine,
+              double i8_mult, void* __restrict__ dst, float* __restrict__ norms_out) {
+    __shared__ float tile[kIngestWarps][32][33];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row0 = ((int64_t)blockIdx.x * kIngestWarps + warp) * 32;
+    if (row0 >= n) return;
+    const int rows_here = (int)min((int64_t)32, n - row0);
+    float (*t)[33] = tile[warp];
+
+    // pass 1: sequential fp64 sum of squares (also needed for ip: stored-row norm bound)
+    double n2 = 0.0;
+    for (int c0 = 0; c0 < dim; c0 += 32) {
+        const int c = c0 + lane;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r)
+            t[r][lane] = (r < rows_here && c < dim) ? src[(row0 + r) * dim + c] : 0.f;
+        __syncwarp();
+        const int cmax = min(32, dim - c0);
+        for (int j = 0; j < cmax; ++j) {
+            const double x = (double)t[lane][j];
+            n2 = fma(x, x, n2);        // x*x is exact in fp64, so fma == mul + add
+        }
+        __syncwarp();
+    }
+    const double norm = sqrt(n2);
+    const double div = (cosine && norm > 0.0) ? norm : 1.0;
+    const bool zero_row = cosine && !(norm > 0.0);
+    if (norms_out && lane < rows_here) {
+        // upper bound of the stored row's norm: unit rows round to <= 1 + 2^-8 (bf16 worst case)
+        const float nb = cosine ? 1.00390625f : __double2float_ru(norm) * 1.00390625f;
+        norms_out[row0 + lane] = nb;
+    }
+
+    // pass 2: normalise + convert, lane = column so stores are coalesced
+    for (int c0 = 0; c0 < dim_padded; c0 += 32) {
+        const int c = c0 + lane;
+#pragma unroll 4
+        for (int r = 0; r < rows_here; ++r) {
+            const double dv = __shfl_sync(CRS_FULL_MASK, div, r);
+            const bool zr = __shfl_sync(CRS_FULL_MASK, (int)zero_row, r) != 0;
+            double y = 0.0;
+            if (c < dim && !zr) y = (double)src[(row0 + r) * dim + c] / dv;
+            const int64_t o = (row0 + r) * (int64_t)dim_padded + c;
+            if constexpr (STORE == CRS_F16) {
+                reinterpret_cast<__half*>(dst)[o] = __double2half(y);
+            } else if constexpr (STORE == CRS_BF16) {
+                reinterpret_cast<__nv_bfloat16*>(dst)[o] = __double2bfloat16(y);
+            } else if constexpr (STORE == CRS_I8) {
+                double q = rint(y * i8_mult);                    // round half to even
+                q = fmin(127.0, fmax(-127.0, q));
+                reinterpret_cast<int8_t*>(dst)[o] = (int8_t)(int)q;
+            } else {   // CRS_B1: bit j%32 of word j/32
+                const unsigned w = __ballot_sync(CRS_FULL_MASK, y > 0.0);
+                if (lane == 0) reinterpret_cast<uint32_t*>(dst)[o >> 5] = w;
+            }
+        }
+    }
+}
+
+cudaError_t launch_encode(cudaStream_t st, const float* src, int64_t n, int dim, int dim_padded,
+                          crs_dtype store, crs_metric metric, float i8_scale, void* dst, float* norms_out) {
+    if (n <= 0) return cudaSuccess;
+    const int64_t rows_per_block = kIngestWarps * 32;
+    const unsigned grid = (unsigned)((n + rows_per_block - 1) / rows_per_block);
+    const int cosine = metric == CRS_COSINE;
+    const double mult = 127.0 / (double)i8_scale;
+    switch (store) {
+        case CRS_F16:  encode_kernel<CRS_F16><<<grid, kIngestWarps * 32, 0, st>>>(src, n, dim, dim_padded, cosine, mult, dst, norms_out); break;
+        case CRS_BF16: encode_kernel<CRS_BF16><<<grid, kIngestWarps * 32, 0, st>>>(src, n, dim, dim_padded, cosine, mult, dst, norms_out); break;
+        case CRS_I8:   encode_kernel<CRS_I8><<<grid, kIngestWarps * 32, 0, st>>>(src, n, dim, dim_padded, cosine, mult, dst, norms_out); break;
+        case CRS_B1:   encode_kernel<CRS_B1><<<grid, kIngestWarps * 32, 0, st>>>(src, n, dim, dim_padded, cosine, mult, dst, norms_out); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+__global__ void gather_rows_kernel(const uint4* __restrict__ codes, int chunks_per_row, int64_t n_rows,
+                                   uint32_t row_base, const uint32_t* __restrict__ ids, int n,
+                                   uint4* __restrict__ out) {
+    const int i = blockIdx.x;
+    if (i >= n) return;
+    const uint32_t gid = ids[i];
+    if (gid < row_base || (int64_t)(gid - row_base) >= n_rows) return;
+    const int64_t r = gid - row_base;
+    for (int c = threadIdx.x; c < chunks_per_row; c += blockDim.x)
+        out[(int64_t)i * chunks_per_row + c] = codes[r * chunks_per_row + c];
+}
+
+cudaError_t launch_gather_rows(cudaStream_t st, const void* codes, size_t row_bytes, int64_t n_rows,
+                               uint32_t row_base, const uint32_t* ids, int n, void* out) {
+    if (n <= 0) return cudaSuccess;
+    gather_rows_kernel<<<n, 64, 0, st>>>(reinterpret_cast<const uint4*>(codes), (int)(row_bytes / 16), n_rows,
+                                         row_base, ids, n, reinterpret_cast<uint4*>(out));
+    return cudaGetLastError();
+}
+
+}  // namespace crs

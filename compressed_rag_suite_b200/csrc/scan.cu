@@ -1,0 +1,281 @@
+// K1 / K2 / K3 — single-query stream scans over the stored rows with fused
+// threshold and in-register top-M.
+//
+// Replaces the O(N*D) distance pass that `collection.query` performs inside
+// ChromaDB for the reference (rag/indexing.py:171-176) with an exhaustive,
+// HBM-bandwidth-bound pass.  Algorithmic bytes per launch: n_rows * row_bytes.
+//
+//   K1  fp16 / bf16 rows : fp32 FMA dot (candidate ranking only, see finalize.cu)
+//   K2  int8 rows        : dp4a, exact int32 dot
+//   K3  1-bit rows       : xor + popc, exact Hamming -> raw = dim - 2h
+//
+// Structure (persistent, one CTA per SM):
+//   * warp NW (producer): one elected lane streams tiles of NW*4*ITERS consecutive
+//     rows with cp.async.bulk (UBLKCP) into a STAGES-deep shared-memory ring,
+//     completion on "full" mbarriers; it re-arms a slot when the NW consumer
+//     warps have arrived on its "empty" mbarrier.
+//   * warps 0..NW-1 (consumers): each takes 4*ITERS rows of the tile, 8 lanes per
+//     row; lane `sub` reads 16-byte chunks sub, sub+8, ... of its row (a
+//     quarter-warp covers 128 contiguous bytes -> conflict-free LDS.128), does the
+//     math against the query held in registers, 3 xor-shuffles finish the dot.
+//     Every row goes through the same instruction sequence, so equal rows get
+//     equal scores.
+//   * candidates: score >= threshold and key > the warp's floor go into a
+//     warp-distributed top-M ("replace the minimum", WarpTopM).  At the end the
+//     warp lists are bitonic-sorted and tree-merged through smem; the CTA writes
+//     one sorted list of M keys.  finalize.cu merges the CTA lists (and, for the
+//     float stores, rescores exactly in fp64 and certifies the result).
+//
+// For fp16/bf16 the score computed here only picks candidates; its error against
+// the canonical fp64 score is bounded by Dp * 2^-24 * |q| * |c| (any summation order).
+#include "common.cuh"
+#include "crs_internal.h"
+
+namespace crs {
+
+constexpr int kScanMaxStages = 16;
+enum ScanKind { kF16 = 0, kBF16 = 1, kI8 = 2, kB1 = 3 };
+
+template <int KIND>
+__device__ __forceinline__ float2 cvt_pair(uint32_t v) {
+    if constexpr (KIND == kBF16) {
+        return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xFFFF0000u));
+    } else {
+        return __half22float2(*reinterpret_cast<const __half2*>(&v));
+    }
+}
+
+// NCH: 128-byte chunk groups per row (row_bytes = 128*NCH).  QREG: query in registers.
+template <int KIND, int NCH, int NW, int ITERS, int LPL, bool QREG>
+__global__ void __launch_bounds__((NW + 1) * 32, 1)
+scan_kernel(const uint8_t* __restrict__ codes, int64_t n_rows, const uint8_t* __restrict__ qcodes,
+            uint32_t ord_min, int32_t b1_dim, uint64_t* __restrict__ cand, int stages) {
+    constexpr bool kFloat = (KIND == kF16 || KIND == kBF16);
+    constexpr int ROWB = NCH * 128;
+    constexpr int ROWS_PER_WARP = 4 * ITERS;
+    constexpr int TILE_ROWS = NW * ROWS_PER_WARP;
+    constexpr int TILE_BYTES = TILE_ROWS * ROWB;
+    constexpr int M = 32 * LPL;
+    constexpr int QN = kFloat ? NCH * 8 : NCH * 4;          // query registers per lane
+
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t full_bar[kScanMaxStages];
+    __shared__ uint64_t empty_bar[kScanMaxStages];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n_tiles = (n_rows + TILE_ROWS - 1) / TILE_ROWS;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NW); }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == NW) {
+        // ------------------------------------------------------------ producer
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                const int64_t r0 = t * TILE_ROWS;
+                const uint32_t bytes = (uint32_t)(min((int64_t)TILE_ROWS, n_rows - r0) * ROWB);
+                mbar_arrive_expect_tx(&full_bar[stage], bytes);
+                bulk_g2s(smem + (size_t)stage * TILE_BYTES, codes + r0 * ROWB, bytes, &full_bar[stage]);
+                if (++stage == stages) { stage = 0; phase ^= 1; }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------- consumers
+    const int sub = lane & 7, grp = lane >> 3;
+    float qf[(kFloat && QREG) ? QN : 1];
+    uint32_t qi[kFloat ? 1 : QN];
+    if constexpr (kFloat && QREG) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const uint4 v = *reinterpret_cast<const uint4*>(qcodes + (c * 8 + sub) * 16);
+            const float2 a = cvt_pair<KIND>(v.x), b = cvt_pair<KIND>(v.y), d = cvt_pair<KIND>(v.z), e = cvt_pair<KIND>(v.w);
+            qf[c * 8 + 0] = a.x; qf[c * 8 + 1] = a.y; qf[c * 8 + 2] = b.x; qf[c * 8 + 3] = b.y;
+            qf[c * 8 + 4] = d.x; qf[c * 8 + 5] = d.y; qf[c * 8 + 6] = e.x; qf[c * 8 + 7] = e.y;
+        }
+    }
+    if constexpr (!kFloat) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const uint4 v = *reinterpret_cast<const uint4*>(qcodes + (c * 8 + sub) * 16);
+            qi[c * 4 + 0] = v.x; qi[c * 4 + 1] = v.y; qi[c * 4 + 2] = v.z; qi[c * 4 + 3] = v.w;
+        }
+    }
+
+    WarpTopM<LPL> top; top.init();
+
+    int stage = 0; uint32_t phase = 0;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        mbar_wait(&full_bar[stage], phase);
+        const uint8_t* tile = smem + (size_t)stage * TILE_BYTES;
+        uint32_t ord[ITERS];
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+            const int row_in_tile = warp * ROWS_PER_WARP + it * 4 + grp;
+            const int64_t row = t * TILE_ROWS + row_in_tile;
+            const uint8_t* rp = tile + (size_t)row_in_tile * ROWB + sub * 16;
+            if constexpr (kFloat) {
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                if (row < n_rows) {          // rows past the end of a partial tile were not copied
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(rp + c * 128);
+                        const float2 f0 = cvt_pair<KIND>(v.x), f1 = cvt_pair<KIND>(v.y), f2 = cvt_pair<KIND>(v.z), f3 = cvt_pair<KIND>(v.w);
+                        if constexpr (QREG) {
+                            a0 = fmaf(f0.x, qf[c * 8 + 0], a0); a1 = fmaf(f0.y, qf[c * 8 + 1], a1);
+                            a2 = fmaf(f1.x, qf[c * 8 + 2], a2); a3 = fmaf(f1.y, qf[c * 8 + 3], a3);
+                            a0 = fmaf(f2.x, qf[c * 8 + 4], a0); a1 = fmaf(f2.y, qf[c * 8 + 5], a1);
+                            a2 = fmaf(f3.x, qf[c * 8 + 6], a2); a3 = fmaf(f3.y, qf[c * 8 + 7], a3);
+                        } else {
+                            const uint4 w = *reinterpret_cast<const uint4*>(qcodes + (c * 8 + sub) * 16);
+                            const float2 g0 = cvt_pair<KIND>(w.x), g1 = cvt_pair<KIND>(w.y), g2 = cvt_pair<KIND>(w.z), g3 = cvt_pair<KIND>(w.w);
+                            a0 = fmaf(f0.x, g0.x, a0); a1 = fmaf(f0.y, g0.y, a1);
+                            a2 = fmaf(f1.x, g1.x, a2); a3 = fmaf(f1.y, g1.y, a3);
+                            a0 = fmaf(f2.x, g2.x, a0); a1 = fmaf(f2.y, g2.y, a1);
+                            a2 = fmaf(f3.x, g3.x, a2); a3 = fmaf(f3.y, g3.y, a3);
+                        }
+                    }
+                }
+                float s = (a0 + a1) + (a2 + a3);
+                s += __shfl_xor_sync(CRS_FULL_MASK, s, 1);
+                s += __shfl_xor_sync(CRS_FULL_MASK, s, 2);
+                s += __shfl_xor_sync(CRS_FULL_MASK, s, 4);
+                ord[it] = orderable_f32(s);
+            } else {
+                int acc = 0;
+                if (row < n_rows) {
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(rp + c * 128);
+                        if constexpr (KIND == kI8) {
+                            acc = __dp4a((int)v.x, (int)qi[c * 4 + 0], acc);
+                            acc = __dp4a((int)v.y, (int)qi[c * 4 + 1], acc);
+                            acc = __dp4a((int)v.z, (int)qi[c * 4 + 2], acc);
+                            acc = __dp4a((int)v.w, (int)qi[c * 4 + 3], acc);
+                        } else {
+                            acc += __popc(v.x ^ qi[c * 4 + 0]) + __popc(v.y ^ qi[c * 4 + 1]) +
+                                   __popc(v.z ^ qi[c * 4 + 2]) + __popc(v.w ^ qi[c * 4 + 3]);
+                        }
+                    }
+                }
+                acc += __shfl_xor_sync(CRS_FULL_MASK, acc, 1);
+                acc += __shfl_xor_sync(CRS_FULL_MASK, acc, 2);
+                acc += __shfl_xor_sync(CRS_FULL_MASK, acc, 4);
+                if constexpr (KIND == kB1) acc = b1_dim - 2 * acc;
+                ord[it] = orderable_i32(acc);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);      // data is in registers: free the slot
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+            const int64_t row = t * TILE_ROWS + warp * ROWS_PER_WARP + it * 4 + grp;
+            const uint64_t key = make_key(ord[it], (uint32_t)row);
+            const bool pass = (sub == 0) && (row < n_rows) && (ord[it] >= ord_min) && (key > top.floor_key);
+            unsigned bal = __ballot_sync(CRS_FULL_MASK, pass);
+            while (bal) {
+                const int src = __ffs(bal) - 1;
+                bal &= bal - 1;
+                const uint64_t kb = shfl_u64(key, src);
+                if (kb > top.floor_key) top.insert(kb, lane);
+            }
+        }
+    }
+
+    // ------------------------------------------------- CTA reduction of the warp lists
+    warp_sort_desc<LPL>(top.e, lane);
+    // every consumer has passed its last full-barrier wait, so all copies have landed
+    // and the ring can be reused as merge scratch once all consumers are here.
+    named_barrier_1<NW * 32>();
+    uint64_t* stage_keys = reinterpret_cast<uint64_t*>(smem);
+    block_merge_lists<LPL, NW>(top.e, stage_keys, warp, lane);
+    if (warp == 0) {
+#pragma unroll
+        for (int sl = 0; sl < LPL; ++sl)
+            cand[(size_t)blockIdx.x * M + lane * LPL + sl] = top.e[sl];
+    }
+}
+
+template <int KIND, int NCH, int NW, int ITERS, int LPL, bool QREG>
+static cudaError_t launch_one(cudaStream_t st, const void* codes, int64_t n, const void* qcodes, uint32_t ord_min,
+                              int32_t b1_dim, uint64_t* cand, int grid) {
+    constexpr int TILE_BYTES = NW * 4 * ITERS * NCH * 128;
+    constexpr int M = 32 * LPL;
+    int stages = (200 * 1024) / TILE_BYTES;
+    if (stages > kScanMaxStages) stages = kScanMaxStages;
+    if (stages < 2) return cudaErrorInvalidConfiguration;
+    size_t smem = (size_t)stages * TILE_BYTES;
+    const size_t merge_bytes = (size_t)NW * M * sizeof(uint64_t);
+    if (smem < merge_bytes) smem = merge_bytes;
+    auto kern = scan_kernel<KIND, NCH, NW, ITERS, LPL, QREG>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, (NW + 1) * 32, smem, st>>>(reinterpret_cast<const uint8_t*>(codes), n,
+                                            reinterpret_cast<const uint8_t*>(qcodes), ord_min, b1_dim, cand, stages);
+    return cudaGetLastError();
+}
+
+template <int KIND, int NCH, int NW, int ITERS, bool QREG>
+static cudaError_t by_lpl(cudaStream_t st, const void* codes, int64_t n, const void* qcodes, uint32_t ord_min,
+                          int32_t b1_dim, uint64_t* cand, const ScanPlan& p) {
+    if (p.lpl == 1) return launch_one<KIND, NCH, NW, ITERS, 1, QREG>(st, codes, n, qcodes, ord_min, b1_dim, cand, p.grid);
+    if (p.lpl == 4) return launch_one<KIND, NCH, NW, ITERS, 4, QREG>(st, codes, n, qcodes, ord_min, b1_dim, cand, p.grid);
+    return cudaErrorInvalidValue;
+}
+
+template <int KIND>
+static cudaError_t by_rowbytes_float(cudaStream_t st, const void* codes, int64_t n, int nch, const void* qcodes,
+                                     uint32_t ord_min, uint64_t* cand, const ScanPlan& p) {
+    switch (nch) {   // row_bytes = 128 * nch, Dp = 64 * nch
+        case 1:  return by_lpl<KIND, 1, 16, 4, true>(st, codes, n, qcodes, ord_min, 0, cand, p);
+        case 2:  return by_lpl<KIND, 2, 16, 2, true>(st, codes, n, qcodes, ord_min, 0, cand, p);
+        case 3:  return by_lpl<KIND, 3, 16, 1, true>(st, codes, n, qcodes, ord_min, 0, cand, p);
+        case 4:  return by_lpl<KIND, 4, 16, 1, true>(st, codes, n, qcodes, ord_min, 0, cand, p);
+        case 6:  return by_lpl<KIND, 6, 16, 1, true>(st, codes, n, qcodes, ord_min, 0, cand, p);
+        case 8:  return by_lpl<KIND, 8, 8, 1, true>(st, codes, n, qcodes, ord_min, 0, cand, p);
+        case 12: return by_lpl<KIND, 12, 8, 1, false>(st, codes, n, qcodes, ord_min, 0, cand, p);
+        case 16: return by_lpl<KIND, 16, 8, 1, false>(st, codes, n, qcodes, ord_min, 0, cand, p);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_scan_f16(cudaStream_t st, const void* codes, int64_t n, int dim_padded, bool bf16,
+                            const void* qcodes, float tau_pre, uint64_t* cand, const ScanPlan& plan) {
+    const uint32_t ord_min = orderable_f32(tau_pre);
+    return bf16 ? by_rowbytes_float<kBF16>(st, codes, n, dim_padded / 64, qcodes, ord_min, cand, plan)
+                : by_rowbytes_float<kF16>(st, codes, n, dim_padded / 64, qcodes, ord_min, cand, plan);
+}
+
+template <int KIND>
+static cudaError_t by_rowbytes_int(cudaStream_t st, const void* codes, int64_t n, int nch, const void* qcodes,
+                                   uint32_t ord_min, int32_t b1_dim, uint64_t* cand, const ScanPlan& p) {
+    switch (nch) {   // row_bytes = 128 * nch
+        case 1:  return by_lpl<KIND, 1, 16, 8, true>(st, codes, n, qcodes, ord_min, b1_dim, cand, p);
+        case 2:  return by_lpl<KIND, 2, 16, 4, true>(st, codes, n, qcodes, ord_min, b1_dim, cand, p);
+        case 3:  return by_lpl<KIND, 3, 16, 2, true>(st, codes, n, qcodes, ord_min, b1_dim, cand, p);
+        case 4:  return by_lpl<KIND, 4, 16, 2, true>(st, codes, n, qcodes, ord_min, b1_dim, cand, p);
+        case 6:  return by_lpl<KIND, 6, 16, 1, true>(st, codes, n, qcodes, ord_min, b1_dim, cand, p);
+        case 8:  return by_lpl<KIND, 8, 16, 1, true>(st, codes, n, qcodes, ord_min, b1_dim, cand, p);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_scan_i8(cudaStream_t st, const void* codes, int64_t n, int dim_padded,
+                           const void* qcodes, int32_t min_raw, uint64_t* cand, const ScanPlan& plan) {
+    return by_rowbytes_int<kI8>(st, codes, n, dim_padded / 128, qcodes, orderable_i32(min_raw), 0, cand, plan);
+}
+
+cudaError_t launch_scan_b1(cudaStream_t st, const void* codes, int64_t n, int dim_padded, int dim,
+                           const void* qcodes, int32_t min_raw, uint64_t* cand, const ScanPlan& plan) {
+    return by_rowbytes_int<kB1>(st, codes, n, dim_padded / 1024, qcodes, orderable_i32(min_raw), dim, cand, plan);
+}
+
+}  // namespace crs

@@ -1,0 +1,199 @@
+"""ShardIndex — Python handle on one ``crs_index`` (one GPU shard of the corpus).
+
+Thin plumbing over the C ABI: numpy arrays go through the host-buffer form of each
+call (the library copies and synchronises), torch CUDA tensors through the
+device-buffer form (the call only enqueues on torch's current stream).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _native as N
+
+
+def _is_torch_cuda(x) -> bool:
+    return type(x).__module__.startswith("torch") and hasattr(x, "is_cuda") and x.is_cuda
+
+
+class ShardIndex:
+    def __init__(self, dim: int, dtype: str = "f16", metric: str = "cosine", device: int = 0,
+                 row_base: int = 0, reserve_rows: int = 0, _handle=None):
+        self._lib = N.lib()
+        self._h = C.c_void_p()
+        if _handle is not None:
+            self._h = _handle
+        else:
+            if dtype not in ("f16", "bf16", "i8", "b1"):
+                raise ValueError(f"dtype must be f16, bf16, i8 or b1, got {dtype!r}")
+            if metric not in N.METRIC_CODES:
+                raise ValueError(f"metric must be cosine or ip, got {metric!r}")
+            N.check(self._lib.crs_index_create(C.byref(self._h), int(dim), N.DTYPE_CODES[dtype],
+                                               N.METRIC_CODES[metric], int(device), int(row_base),
+                                               int(reserve_rows)))
+        d, dp, rb, st, me = C.c_int32(), C.c_int32(), C.c_int64(), C.c_int32(), C.c_int32()
+        N.check(self._lib.crs_index_info(self._h, C.byref(d), C.byref(dp), C.byref(rb), C.byref(st), C.byref(me)))
+        self.dim, self.dim_padded, self.row_bytes = d.value, dp.value, rb.value
+        self.dtype = {v: k for k, v in N.DTYPE_CODES.items()}[st.value]
+        self.metric = {v: k for k, v in N.METRIC_CODES.items()}[me.value]
+        self.device = int(device)
+        self.row_base = int(row_base)
+        sc = C.c_double()
+        N.check(self._lib.crs_index_similarity_scale(self._h, C.byref(sc)))
+        self.similarity_scale = sc.value
+        self.is_int = self.dtype in ("i8", "b1")
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self) -> None:
+        if self._h:
+            self._lib.crs_index_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self) -> int:
+        n = C.c_int64()
+        N.check(self._lib.crs_index_count(self._h, C.byref(n)))
+        return n.value
+
+    def _use_torch_stream(self) -> None:
+        import torch
+        N.check(self._lib.crs_index_set_stream(self._h, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+
+    def set_option(self, name: str, value: int) -> None:
+        N.check(self._lib.crs_index_set_option(self._h, name.encode(), int(value)))
+
+    def last_stats(self) -> dict:
+        s = N.SearchStats()
+        N.check(self._lib.crs_index_last_stats(self._h, C.byref(s)))
+        return {f: getattr(s, f) for f, _ in s._fields_}
+
+    # ------------------------------------------------------------------ ingest
+    def add(self, rows) -> None:
+        """rows: float32 [n, dim] numpy array (host) or torch CUDA tensor (device)."""
+        if _is_torch_cuda(rows):
+            import torch
+            if rows.dtype != torch.float32 or rows.dim() != 2 or rows.shape[1] != self.dim:
+                raise ValueError(f"rows must be float32 [n, {self.dim}]")
+            rows = rows.contiguous()
+            self._use_torch_stream()
+            N.check(self._lib.crs_index_add(self._h, C.c_void_p(rows.data_ptr()), rows.shape[0], N.CRS_F32))
+            return
+        a = np.ascontiguousarray(rows, dtype=np.float32)
+        if a.ndim != 2 or a.shape[1] != self.dim:
+            raise ValueError(f"rows must be float32 [n, {self.dim}], got {a.shape}")
+        N.check(self._lib.crs_index_add(self._h, a.ctypes.data_as(C.c_void_p), a.shape[0], N.CRS_F32))
+
+    # ------------------------------------------------------------------ search
+    def search(self, queries, k: int, min_similarity: float = -math.inf):
+        """-> (ids uint32 [nq,k], raw scores f32|i32 [nq,k], counts i32 [nq]).
+
+        numpy in -> numpy out (synchronous); torch CUDA in -> torch CUDA out (enqueued on
+        the current stream).  ids are global row ids, padded with 0xFFFFFFFF."""
+        if _is_torch_cuda(queries):
+            import torch
+            q = queries
+            if q.dim() == 1:
+                q = q[None, :]
+            if q.dtype != torch.float32 or q.shape[1] != self.dim:
+                raise ValueError(f"queries must be float32 [nq, {self.dim}]")
+            q = q.contiguous()
+            nq = q.shape[0]
+            dev = q.device
+            # torch has no uint32 arithmetic: ids travel as int32 bit patterns
+            ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
+            sc = torch.empty((nq, k), dtype=torch.int32 if self.is_int else torch.float32, device=dev)
+            cnt = torch.empty((nq,), dtype=torch.int32, device=dev)
+            self._use_torch_stream()
+            N.check(self._lib.crs_index_search(self._h, C.c_void_p(q.data_ptr()), nq, int(k), float(min_similarity),
+                                               C.c_void_p(ids.data_ptr()), C.c_void_p(sc.data_ptr()),
+                                               C.c_void_p(cnt.data_ptr())))
+            return ids, sc, cnt
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"queries must be float32 [nq, {self.dim}], got {q.shape}")
+        nq = q.shape[0]
+        ids = np.empty((nq, k), dtype=np.uint32)
+        sc = np.empty((nq, k), dtype=np.int32 if self.is_int else np.float32)
+        cnt = np.empty((nq,), dtype=np.int32)
+        N.check(self._lib.crs_index_search(self._h, q.ctypes.data_as(C.c_void_p), nq, int(k), float(min_similarity),
+                                           ids.ctypes.data_as(C.c_void_p), sc.ctypes.data_as(C.c_void_p),
+                                           cnt.ctypes.data_as(C.c_void_p)))
+        return ids, sc, cnt
+
+    def similarity(self, raw):
+        """raw scores -> float32 cosine-domain similarity (numpy)."""
+        raw = np.asarray(raw)
+        if self.dtype == "i8":
+            return raw.astype(np.float32) * np.float32(self.similarity_scale)
+        if self.dtype == "b1":
+            return (raw.astype(np.float64) / float(self.dim)).astype(np.float32)
+        return raw.astype(np.float32)
+
+    # ------------------------------------------------------------------ candidate vectors / MMR
+    def code_dtype(self):
+        return {"f16": np.float16, "bf16": np.uint16, "i8": np.int8, "b1": np.uint32}[self.dtype]
+
+    def fetch_rows(self, ids, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Stored codes of the given global row ids -> [n, row_bytes] uint8 (host).
+        Rows owned by other shards are left as they are in ``out`` (zeros by default)."""
+        ids = np.ascontiguousarray(ids, dtype=np.uint32).reshape(-1)
+        if out is None:
+            out = np.zeros((ids.shape[0], self.row_bytes), dtype=np.uint8)
+        N.check(self._lib.crs_index_fetch_rows(self._h, ids.ctypes.data_as(C.c_void_p), ids.shape[0],
+                                               out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def mmr(self, vecs: np.ndarray, relevance, lam: float, k_out: Optional[int] = None) -> np.ndarray:
+        """Greedy MMR order.  vecs: [nq, m, row_bytes] uint8 stored codes (or [m, row_bytes]);
+        relevance: [nq, m] float64.  -> int32 [nq, k_out] positions."""
+        v = np.ascontiguousarray(vecs, dtype=np.uint8)
+        if v.ndim == 2:
+            v = v[None]
+        r = np.ascontiguousarray(relevance, dtype=np.float64).reshape(v.shape[0], -1)
+        nq, m = r.shape
+        if v.shape[1] != m or v.shape[2] != self.row_bytes:
+            raise ValueError("vecs must be [nq, m, row_bytes]")
+        k_out = m if k_out is None else int(k_out)
+        out = np.empty((nq, k_out), dtype=np.int32)
+        N.check(self._lib.crs_mmr(self._h, v.ctypes.data_as(C.c_void_p), r.ctypes.data_as(C.c_void_p), nq, m, k_out,
+                                  float(lam), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    # ------------------------------------------------------------------ persistence
+    def save(self, path: str) -> None:
+        N.check(self._lib.crs_index_save(self._h, path.encode()))
+
+    @classmethod
+    def load(cls, path: str, device: int = 0, row_base: int = 0) -> "ShardIndex":
+        lib = N.lib()
+        h = C.c_void_p()
+        N.check(lib.crs_index_load(C.byref(h), path.encode(), int(device), int(row_base)))
+        return cls(0, device=device, row_base=row_base, _handle=h)
+
+
+def merge_topk(ids, scores, k_out: int):
+    """K7 on torch CUDA tensors: ids int32 [G, nq, k_in] (uint32 bit patterns), scores
+    f32|i32 [G, nq, k_in] -> (ids [nq,k_out], scores [nq,k_out], counts [nq])."""
+    import torch
+    g, nq, k_in = ids.shape
+    ids = ids.contiguous()
+    scores = scores.contiguous()
+    is_int = scores.dtype == torch.int32
+    out_ids = torch.empty((nq, k_out), dtype=torch.int32, device=ids.device)
+    out_sc = torch.empty((nq, k_out), dtype=scores.dtype, device=ids.device)
+    out_cnt = torch.empty((nq,), dtype=torch.int32, device=ids.device)
+    st = torch.cuda.current_stream(ids.device).cuda_stream
+    N.check(N.lib().crs_merge_topk(C.c_void_p(st), C.c_void_p(ids.data_ptr()), C.c_void_p(scores.data_ptr()),
+                                   int(is_int), g, nq, k_in, int(k_out), C.c_void_p(out_ids.data_ptr()),
+                                   C.c_void_p(out_sc.data_ptr()), C.c_void_p(out_cnt.data_ptr())))
+    return out_ids, out_sc, out_cnt

@@ -1,0 +1,131 @@
+/* crs.h — C ABI of libcrs.so: exact similarity search on B200 (sm_100a).
+ *
+ * This is the drop-in boundary for the one hot path of
+ * zahraamselim/compressed-rag-suite that this repository replaces: the calls
+ * `rag/indexing.py` makes into ChromaDB and the numeric half of
+ * `rag/retrieval.py`.  Every entry point names the reference interface it
+ * replaces (paths relative to the reference tree).  The reference is Python and
+ * binds nothing native today; a maintainer would bind these symbols with the
+ * ctypes stub shown in INTEGRATION.md (that stub is what
+ * compressed_rag_suite_b200/_native.py ships).
+ *
+ * Conventions
+ *  - plain C, no exceptions across the boundary: every function returns 0
+ *    (CRS_OK) or a CRS_E* code; crs_last_error() gives the thread-local message.
+ *    The Python host turns a non-zero status into the ValueError/RuntimeError
+ *    the reference raises after logging (rag/indexing.py:121-123,178-180).
+ *  - one index = one GPU shard (one process per GPU; cross-GPU exchange is done
+ *    by the host with torch.distributed/NCCL and crs_merge_topk).  Row ids are
+ *    uint32 insertion indices, global id = row_base + local row.
+ *  - in/out buffers belong to the caller and may be host or device pointers
+ *    (detected with cudaPointerGetAttributes).  With device buffers a call only
+ *    enqueues work on the index's stream (crs_index_set_stream); with host
+ *    buffers it returns after the results are in the host buffer.
+ *  - calls on one index are serialised by an internal mutex.
+ *  - there is no CPU implementation behind these symbols: without a usable
+ *    sm_100 device crs_index_create fails with CRS_ECUDA.
+ */
+#ifndef CRS_H_
+#define CRS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct crs_index crs_index;
+
+typedef enum { CRS_F32 = 0, CRS_F16 = 1, CRS_BF16 = 2, CRS_I8 = 3, CRS_B1 = 4 } crs_dtype;
+/* Chroma "hnsw:space" values the reference can meet (rag/indexing.py:83 always
+ * creates "cosine"; rag/retrieval.py:84-87 also knows "ip"). */
+typedef enum { CRS_COSINE = 0, CRS_IP = 1 } crs_metric;
+
+enum { CRS_OK = 0, CRS_EINVAL = 1, CRS_ECUDA = 2, CRS_ENOMEM = 3, CRS_ESTATE = 4, CRS_EIO = 5 };
+
+#define CRS_PAD_ID 0xFFFFFFFFu
+
+/* Counters of the last crs_index_search on an index (bench.py's gpu_launches). */
+typedef struct crs_search_stats {
+    int32_t kernel_launches;   /* kernels of libcrs launched by the call */
+    int32_t path;              /* 0 = stream scan (K1/K2/K3), 1 = tcgen05 GEMM (K4/K5) */
+    int32_t grid;              /* CTAs of the dominant kernel */
+    int32_t list_len;          /* candidates kept per query per CTA (M) */
+    int64_t uncertified_total; /* float stores: queries that needed the exact fp64 pass, since create */
+    int64_t searches_total;
+} crs_search_stats;
+
+const char* crs_last_error(void);
+int crs_version(void);
+
+/* replaces chromadb.Client()/PersistentClient() + client.create_collection(name,
+ * metadata={"hnsw:space": ...})  — rag/indexing.py:31-37,81-84.
+ *   store        : F16 | BF16 | I8 | B1 (how rows are kept in HBM)
+ *   device       : CUDA ordinal;  row_base: global id of local row 0
+ *   reserve_rows : capacity hint (0 = grow on demand) */
+int crs_index_create(crs_index** out, int dim, crs_dtype store, crs_metric metric,
+                     int device, uint32_t row_base, int64_t reserve_rows);
+/* replaces client.delete_collection(name) — rag/indexing.py:186 */
+int crs_index_destroy(crs_index* idx);
+/* cudaStream_t the index enqueues on (NULL = default stream). */
+int crs_index_set_stream(crs_index* idx, void* cuda_stream);
+
+/* replaces collection.add(embeddings=...) — rag/indexing.py:114-119 (the
+ * ids/documents/metadatas of that call stay with the Python host).
+ *   rows: [n, dim] row-major, src_dtype must be CRS_F32; host or device. */
+int crs_index_add(crs_index* idx, const void* rows, int64_t n, crs_dtype src_dtype);
+/* replaces collection.count() — rag/indexing.py:52,120,147,152,206 */
+int crs_index_count(const crs_index* idx, int64_t* out_count);
+/* dim, padded dim, bytes per stored row, store dtype, metric */
+int crs_index_info(const crs_index* idx, int32_t* dim, int32_t* dim_padded, int64_t* row_bytes,
+                   int32_t* store, int32_t* metric);
+
+/* replaces collection.query(query_embeddings, n_results) — rag/indexing.py:171-176 —
+ * plus the similarity_threshold filter of rag/retrieval.py:143 pushed down as
+ * min_similarity (cosine/dot domain, -INFINITY = off).
+ *   queries    : [nq, dim] fp32, host or device
+ *   out_ids    : [nq, k] global row ids, descending score, ties -> lowest id, CRS_PAD_ID padded
+ *   out_scores : [nq, k] raw inner product of the stored codes — float32 for F16/BF16,
+ *                int32 for I8 (dot) and B1 (dim - 2*hamming); pad = -inf / INT32_MIN
+ *   out_counts : [nq] number of valid entries per query */
+int crs_index_search(crs_index* idx, const void* queries, int nq, int k, float min_similarity,
+                     uint32_t* out_ids, void* out_scores, int32_t* out_counts);
+int crs_index_last_stats(const crs_index* idx, crs_search_stats* out);
+/* Tuning / test hooks: name in {"force_path" (-1 auto, 0 scan, 1 gemm), "force_exact"
+ * (1 = always run the fp64 pass), "eps_scale" (x1000)}. */
+int crs_index_set_option(crs_index* idx, const char* name, int64_t value);
+
+/* raw -> float similarity scale of this index: sim = raw * scale (1 for F16/BF16,
+ * (a/127)^2 for I8, 1/dim for B1). */
+int crs_index_similarity_scale(const crs_index* idx, double* out_scale);
+
+/* copies stored rows (codes, row_bytes each) of global ids into out; ids outside this
+ * shard are skipped (their output rows are left untouched).  Feeds crs_mmr. */
+int crs_index_fetch_rows(crs_index* idx, const uint32_t* ids, int n, void* out_codes);
+
+/* replaces ContextRetriever._apply_diversity — rag/retrieval.py:219-277 — on stored
+ * vectors instead of re-embedded texts.
+ *   vecs      : [nq, m, row_bytes] stored codes of the m candidates (position order)
+ *   relevance : [nq, m] the chunks' `score` values (Python floats -> double)
+ *   lambda    : 1 - diversity_penalty
+ *   out_order : [nq, k_out] positions 0..m-1 in greedy MMR order (first = position 0) */
+int crs_mmr(crs_index* idx, const void* vecs, const double* relevance, int nq, int m, int k_out,
+            double lambda, int32_t* out_order);
+
+/* cross-shard merge after the allgather of local top-k lists (no reference
+ * counterpart: the reference is single-node).
+ *   ids/scores : [n_lists, nq, k_in] device pointers;  is_int: scores are int32 */
+int crs_merge_topk(void* cuda_stream, const uint32_t* ids, const void* scores, int is_int,
+                   int n_lists, int nq, int k_in, int k_out,
+                   uint32_t* out_ids, void* out_scores, int32_t* out_counts);
+
+/* replaces chromadb.PersistentClient(path) persistence + get_collection reload —
+ * rag/indexing.py:32-34,46-55.  Raw code blob + small header; the host keeps
+ * ids/documents/metadatas in a sidecar. */
+int crs_index_save(crs_index* idx, const char* path);
+int crs_index_load(crs_index** out, const char* path, int device, uint32_t row_base);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRS_H_ */

@@ -1,0 +1,260 @@
+"""GPU tier (-m gpu): the CUDA path, called through the C ABI, against the oracle.
+
+Bit-exact for ids, raw scores (float stores: fl32 of the fp64-sequential dot), counts,
+stored codes and MMR order.  The only tolerance in this file is the 1e-3 the north star
+allows between the canonical fp16 score and the plain fp32 brute force on the original
+fp32 embeddings."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import clustered, queries_for
+from oracle import encode, postprocess, search
+
+pytestmark = pytest.mark.gpu
+
+from compressed_rag_suite_b200.index import ShardIndex  # noqa: E402
+
+
+def as_codes(raw_bytes, store, dp):
+    dt = {"f16": np.float16, "bf16": np.uint16, "i8": np.int8, "b1": np.uint32}[store]
+    return raw_bytes.view(dt).reshape(raw_bytes.shape[0], -1)
+
+
+# ---------------------------------------------------------------- K0 ingest
+@pytest.mark.parametrize("store", ["f16", "bf16", "i8", "b1"])
+@pytest.mark.parametrize("dim", [384, 100, 64, 1000])
+def test_ingest_bit_exact(store, dim):
+    rng = np.random.default_rng(dim)
+    n = 517                                        # ragged: not a multiple of the 32-row warp tile
+    x = (rng.standard_normal((n, dim)) * np.exp(rng.uniform(-3, 3, (n, 1)))).astype(np.float32)
+    x[7] = 0.0                                     # zero row stays zero
+    x[8, :] = 0.0
+    x[8, 3] = -2.5
+    ix = ShardIndex(dim, dtype=store)
+    ix.add(x[:200])
+    ix.add(x[200:])                                # two adds, second one unaligned
+    assert len(ix) == n
+    got = as_codes(ix.fetch_rows(np.arange(n)), store, ix.dim_padded)
+    want = encode.encode_rows(x, store)
+    assert ix.dim_padded == encode.padded_dim(dim, store)
+    assert got.shape == want.shape
+    assert np.array_equal(got.view(np.uint8), want.view(np.uint8))
+
+
+def test_ingest_ip_metric_keeps_values():
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((100, 128)).astype(np.float32) * 3
+    ix = ShardIndex(128, dtype="f16", metric="ip")
+    ix.add(x)
+    got = as_codes(ix.fetch_rows(np.arange(100)), "f16", 128)
+    assert np.array_equal(got, encode.encode_rows(x, "f16", "ip"))
+
+
+def test_ingest_from_device_tensor():
+    import torch
+    rng = np.random.default_rng(6)
+    x = rng.standard_normal((1000, 384)).astype(np.float32)
+    ix = ShardIndex(384)
+    ix.add(torch.from_numpy(x).cuda())
+    got = as_codes(ix.fetch_rows(np.arange(1000)), "f16", 384)
+    assert np.array_equal(got, encode.encode_rows(x, "f16"))
+
+
+# ---------------------------------------------------------------- K1/K2/K3 + finalize
+def check_search(ix, x, q, store, k, min_similarity=-np.inf, row_base=0):
+    dim = x.shape[1]
+    codes = encode.encode_rows(x, store, ix.metric)
+    qc = search.encode_queries(q, store, ix.metric)
+    want = search.search(codes, qc, store, dim, k, min_similarity, row_base=row_base)
+    got = ix.search(q, k, min_similarity)
+    assert np.array_equal(got[2], want[2]), "counts differ"
+    assert np.array_equal(got[0], want[0]), "ids differ"
+    assert np.array_equal(got[1].view(np.uint32), want[1].view(np.uint32)), "raw scores differ"
+    return got
+
+
+@pytest.mark.parametrize("store", ["f16", "bf16", "i8", "b1"])
+@pytest.mark.parametrize("n,dim,k", [(20000, 384, 10), (5003, 384, 3), (777, 128, 16), (40000, 256, 100),
+                                     (3000, 1024, 10), (9, 384, 5), (150, 384, 32)])
+def test_search_bit_exact(store, n, dim, k):
+    if store in ("f16", "bf16") and k > 16 and k > n:
+        pytest.skip("covered elsewhere")
+    x, centres = clustered(n, dim, seed=n + dim)
+    q = queries_for(centres, x, 5, seed=k)
+    ix = ShardIndex(dim, dtype=store)
+    ix.add(x)
+    kk = min(k, n)
+    check_search(ix, x, q, store, kk)
+
+
+@pytest.mark.parametrize("store", ["f16", "i8", "b1"])
+def test_search_threshold_and_count_lt_k(store):
+    x, centres = clustered(30000, 384, seed=77)
+    q = queries_for(centres, x, 6, seed=78)
+    ix = ShardIndex(384, dtype=store)
+    ix.add(x)
+    for thr in (-0.1832, 0.293, 0.45, 0.9999, 1.5):
+        got = check_search(ix, x, q, store, 10, min_similarity=thr)
+    assert got[2].max() == 0                       # nothing reaches 1.5
+
+
+def test_search_ties_lowest_id_and_duplicates():
+    x, centres = clustered(8000, 384, seed=90, dup_frac=0.0)
+    for dst in (11, 4000, 7999, 512, 513, 514):
+        x[dst] = x[10]                             # seven identical rows
+    q = np.stack([x[10], x[10] * 3.0, x[4000] + 1e-4 * x[1]])
+    ix = ShardIndex(384)
+    ix.add(x)
+    ids, raw, cnt = check_search(ix, x, q, "f16", 10)
+    assert list(ids[0][:7]) == [10, 11, 512, 513, 514, 4000, 7999]
+    assert len(set(raw[0][:7].tolist())) == 1
+
+
+def test_many_duplicates_take_the_exact_fallback():
+    """More equal rows than the candidate list can hold: certification must fail and the
+    exhaustive fp64 pass must still give the lowest ids."""
+    x, centres = clustered(6000, 384, seed=91, dup_frac=0.0)
+    x[100:180] = x[5]                              # 81 identical rows > M = 32
+    q = np.stack([x[5], x[3000]])
+    ix = ShardIndex(384)
+    ix.add(x)
+    ids, raw, cnt = check_search(ix, x, q, "f16", 10)
+    assert list(ids[0]) == [5] + list(range(100, 109))
+    assert ix.last_stats()["uncertified_total"] >= 1
+
+
+def test_forced_exact_pass_equals_fast_pass():
+    x, centres = clustered(12000, 384, seed=92)
+    q = queries_for(centres, x, 4, seed=93)
+    ix = ShardIndex(384)
+    ix.add(x)
+    fast = ix.search(q, 10)
+    ix.set_option("force_exact", 1)
+    slow = check_search(ix, x, q, "f16", 10)
+    for a, b in zip(fast, slow):
+        assert np.array_equal(a, b)
+
+
+def test_row_base_and_device_buffers():
+    import torch
+    x, centres = clustered(9000, 384, seed=94)
+    q = queries_for(centres, x, 7, seed=95)
+    ix = ShardIndex(384, row_base=1_000_000)
+    ix.add(x)
+    host = check_search(ix, x, q, "f16", 10, row_base=1_000_000)
+    ids, sc, cnt = ix.search(torch.from_numpy(q).cuda(), 10)
+    torch.cuda.synchronize()
+    assert np.array_equal(ids.cpu().numpy().view(np.uint32), host[0])
+    assert np.array_equal(sc.cpu().numpy(), host[1])
+    assert np.array_equal(cnt.cpu().numpy(), host[2])
+
+
+def test_empty_index_and_bad_arguments():
+    ix = ShardIndex(384)
+    ids, raw, cnt = ix.search(np.zeros((2, 384), np.float32), 5)
+    assert cnt.tolist() == [0, 0] and np.all(ids == 0xFFFFFFFF) and np.all(raw == -np.inf)
+    with pytest.raises(ValueError):
+        ix.search(np.zeros((1, 100), np.float32), 5)
+    with pytest.raises(ValueError):
+        ix.add(np.zeros((3, 7), np.float32))
+    with pytest.raises(ValueError):
+        ix.search(np.zeros((1, 384), np.float32), 0)
+    with pytest.raises(ValueError):
+        ShardIndex(384, dtype="f32")
+
+
+def test_fp16_scores_within_1e3_of_fp32_bruteforce():
+    """North-star tolerance: canonical fp16 scores vs plain fp32 brute force on the ORIGINAL
+    fp32 embeddings: |delta| <= 1e-3 absolute; ids agree except on near-ties."""
+    x, centres = clustered(50000, 384, seed=96, dup_frac=0.0)
+    q = queries_for(centres, x, 16, seed=97)
+    ix = ShardIndex(384)
+    ix.add(x)
+    ids, raw, cnt = ix.search(q, 10)
+    bi, bs = search.bruteforce_f32(x, q, 10)
+    assert np.abs(raw - bs).max() <= 1e-3
+    assert np.mean(ids.astype(np.int64) == bi) > 0.9
+
+
+def test_save_load_roundtrip(tmp_path):
+    x, centres = clustered(3000, 384, seed=98)
+    q = queries_for(centres, x, 3, seed=99)
+    for store in ("f16", "i8", "b1"):
+        ix = ShardIndex(384, dtype=store)
+        ix.add(x)
+        want = ix.search(q, 8)
+        p = str(tmp_path / f"{store}.crs")
+        ix.save(p)
+        jx = ShardIndex.load(p)
+        assert (jx.dim, jx.dtype, len(jx)) == (384, store, 3000)
+        got = jx.search(q, 8)
+        for a, b in zip(want, got):
+            assert np.array_equal(a, b)
+
+
+# ---------------------------------------------------------------- K7 merge
+@pytest.mark.parametrize("store", ["f16", "i8"])
+@pytest.mark.parametrize("g,k", [(2, 10), (8, 10), (4, 100), (3, 1)])
+def test_shard_merge_equals_single_index(store, g, k):
+    import torch
+    from compressed_rag_suite_b200.index import merge_topk
+    n = 24000
+    x, centres = clustered(n, 384, seed=100 + g)
+    q = queries_for(centres, x, 9, seed=101)
+    whole = ShardIndex(384, dtype=store)
+    whole.add(x)
+    want = whole.search(q, k)
+    per = (n + g - 1) // g
+    qd = torch.from_numpy(q).cuda()
+    ids_l, sc_l = [], []
+    for r in range(g):
+        sh = ShardIndex(384, dtype=store, row_base=r * per)
+        sh.add(x[r * per:(r + 1) * per])
+        i, s, c = sh.search(qd, k)
+        ids_l.append(i)
+        sc_l.append(s)
+    mi, ms, mc = merge_topk(torch.stack(ids_l), torch.stack(sc_l), k)
+    torch.cuda.synchronize()
+    assert np.array_equal(mi.cpu().numpy().view(np.uint32), want[0])
+    assert np.array_equal(ms.cpu().numpy(), want[1])
+    assert np.array_equal(mc.cpu().numpy(), want[2])
+    # and against the oracle's merge of the oracle's shard results
+    om = search.merge_topk(torch.stack(ids_l).cpu().numpy().view(np.uint32), torch.stack(sc_l).cpu().numpy(), k)
+    assert np.array_equal(om[0], want[0])
+
+
+# ---------------------------------------------------------------- K6 MMR
+def test_mmr_dyadic_golden_bit_exact(golden_dir):
+    """Expected orders were produced by the reference's own _apply_diversity."""
+    cases = json.load(open(os.path.join(golden_dir, "mmr_dyadic_golden.json")))
+    for c in cases:
+        v = np.asarray(c["vectors_x64"], dtype=np.float32) / 64.0
+        ix = ShardIndex(c["dim"], dtype="f16", metric="ip")       # ip: values stored as given
+        ix.add(v)
+        codes = ix.fetch_rows(np.arange(c["m"]))
+        order = ix.mmr(codes, np.asarray(c["relevance"]), 1.0 - c["penalty"])
+        assert order[0].tolist() == c["order"], (c["m"], c["mode"], c["penalty"])
+        half = max(1, c["m"] // 2)
+        assert ix.mmr(codes, np.asarray(c["relevance"]), 1.0 - c["penalty"], k_out=half)[0].tolist() == c["order"][:half]
+
+
+@pytest.mark.parametrize("store", ["f16", "bf16", "i8", "b1"])
+def test_mmr_matches_oracle_on_stored_vectors(store):
+    x, centres = clustered(400, 384, seed=120, n_clusters=5)
+    ix = ShardIndex(384, dtype=store)
+    ix.add(x)
+    rng = np.random.default_rng(121)
+    for m, lam in [(3, 0.9), (20, 0.9), (100, 0.9), (64, 0.5), (7, 0.0)]:
+        rows = rng.choice(400, size=m, replace=False)
+        rel = np.sort(rng.uniform(0.3, 0.95, m))[::-1].copy()
+        codes = ix.fetch_rows(rows)
+        dec = encode.decode_rows(as_codes(codes, store, ix.dim_padded), store)
+        if store == "b1":
+            dec = dec[:, :384]
+        want = postprocess.mmr_order([float(r) for r in rel], postprocess.pairwise_sims_f32(dec), lam,
+                                     k_out=min(m, 10))
+        got = ix.mmr(codes, rel, lam, k_out=min(m, 10))[0].tolist()
+        assert got == want, (store, m, lam)
