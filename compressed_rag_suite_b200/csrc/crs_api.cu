@@ -106,6 +106,9 @@ struct crs_index {
     DevScratch<uint8_t> scores_dev;
     int32_t* n_flagged = nullptr;      // device counters: [0] this search, [1] since create
     crs_search_stats stats{};
+    int profiling = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // bracket the dominant kernel(s) of the last search
+    bool ev_valid = false;
     std::mutex mu;
 };
 
@@ -221,6 +224,8 @@ int crs_index_destroy(crs_index* ix) {
         cudaStreamSynchronize(ix->stream);
         if (ix->codes) cudaFree(ix->codes);
         if (ix->n_flagged) cudaFree(ix->n_flagged);
+        if (ix->ev0) cudaEventDestroy(ix->ev0);
+        if (ix->ev1) cudaEventDestroy(ix->ev1);
         ix->qsrc.release(); ix->qnorms.release(); ix->norms_tmp.release(); ix->qcodes.release();
         ix->stage_rows.release(); ix->cand.release(); ix->flags.release(); ix->counts_dev.release();
         ix->ids_dev.release(); ix->scores_dev.release();
@@ -242,6 +247,14 @@ int crs_index_set_option(crs_index* ix, const char* name, int64_t value) {
     if (!strcmp(name, "force_path")) ix->force_path = (int)value;
     else if (!strcmp(name, "force_exact")) ix->force_exact = (int)value;
     else if (!strcmp(name, "eps_scale")) ix->eps_scale = (double)value / 1000.0;
+    else if (!strcmp(name, "profiling")) {
+        DeviceGuard g(ix->device);
+        ix->profiling = (int)value;
+        if (ix->profiling && !ix->ev0) {
+            CRS_CUDA(cudaEventCreate(&ix->ev0));
+            CRS_CUDA(cudaEventCreate(&ix->ev1));
+        }
+    }
     else return fail(CRS_EINVAL, std::string("unknown option ") + name);
     return CRS_OK;
 }
@@ -321,6 +334,16 @@ int crs_index_last_stats(const crs_index* ix, crs_search_stats* out) {
     DeviceGuard g(ix->device);
     CRS_CUDA(cudaMemcpy(&tot, ix->n_flagged + 1, sizeof(int32_t), cudaMemcpyDeviceToHost));
     out->uncertified_total = tot;
+    return CRS_OK;
+}
+
+int crs_index_last_kernel_ms(crs_index* ix, float* out_ms) {
+    if (!ix || !out_ms) return fail(CRS_EINVAL, "bad argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    if (!ix->profiling || !ix->ev_valid) return fail(CRS_ESTATE, "profiling is off or no search was timed");
+    DeviceGuard g(ix->device);
+    CRS_CUDA(cudaEventSynchronize(ix->ev1));
+    CRS_CUDA(cudaEventElapsedTime(out_ms, ix->ev0, ix->ev1));
     return CRS_OK;
 }
 
@@ -413,12 +436,14 @@ int crs_index_search(crs_index* ix, const void* queries, int nq, int k, float mi
                 float tau_pre = -INFINITY;
                 if (ix->metric == CRS_COSINE && min_similarity > -INFINITY)
                     tau_pre = min_similarity - eps_rel * 1.00390625f * ix->row_norm_bound;
+                if (ix->profiling) CRS_CUDA(cudaEventRecord(ix->ev0, st));
                 for (int q = 0; q < nq; ++q) {
                     CRS_CUDA(crs::launch_scan_f16(st, ix->codes, ix->count, ix->dim_padded, fa.bf16,
                                                   ix->qcodes.p + (size_t)q * ix->row_bytes, tau_pre,
                                                   ix->cand.p + (size_t)q * n_lists * M, plan));
                     ++launches;
                 }
+                if (ix->profiling) { CRS_CUDA(cudaEventRecord(ix->ev1, st)); ix->ev_valid = true; }
                 fa.mode = 0; fa.only_flagged = 0;
                 CRS_CUDA(cudaMemsetAsync(ix->n_flagged, 0, sizeof(int32_t), st));
                 CRS_CUDA(crs::launch_finalize(st, fa));
@@ -447,6 +472,7 @@ int crs_index_search(crs_index* ix, const void* queries, int nq, int k, float mi
             }
         } else {
             const int32_t min_raw = min_raw_for(ix, min_similarity);
+            if (ix->profiling) CRS_CUDA(cudaEventRecord(ix->ev0, st));
             for (int q = 0; q < nq; ++q) {
                 const uint8_t* qc = ix->qcodes.p + (size_t)q * ix->row_bytes;
                 uint64_t* cd = ix->cand.p + (size_t)q * n_lists * M;
@@ -456,6 +482,7 @@ int crs_index_search(crs_index* ix, const void* queries, int nq, int k, float mi
                     CRS_CUDA(crs::launch_scan_b1(st, ix->codes, ix->count, ix->dim_padded, ix->dim, qc, min_raw, cd, plan));
                 ++launches;
             }
+            if (ix->profiling) { CRS_CUDA(cudaEventRecord(ix->ev1, st)); ix->ev_valid = true; }
             fa.mode = 1; fa.only_flagged = 0;
             CRS_CUDA(crs::launch_finalize(st, fa));
             ++launches;

@@ -75,6 +75,12 @@ class ShardIndex:
         N.check(self._lib.crs_index_last_stats(self._h, C.byref(s)))
         return {f: getattr(s, f) for f, _ in s._fields_}
 
+    def last_kernel_ms(self) -> float:
+        """Device time of the dominant kernel(s) of the last search (needs set_option('profiling', 1))."""
+        ms = C.c_float()
+        N.check(self._lib.crs_index_last_kernel_ms(self._h, C.byref(ms)))
+        return ms.value
+
     # ------------------------------------------------------------------ ingest
     def add(self, rows) -> None:
         """rows: float32 [n, dim] numpy array (host) or torch CUDA tensor (device)."""

@@ -92,8 +92,12 @@ int crs_index_search(crs_index* idx, const void* queries, int nq, int k, float m
                      uint32_t* out_ids, void* out_scores, int32_t* out_counts);
 int crs_index_last_stats(const crs_index* idx, crs_search_stats* out);
 /* Tuning / test hooks: name in {"force_path" (-1 auto, 0 scan, 1 gemm), "force_exact"
- * (1 = always run the fp64 pass), "eps_scale" (x1000)}. */
+ * (1 = always run the fp64 pass), "eps_scale" (x1000), "profiling" (1 = bracket the
+ * dominant kernel(s) of each search with CUDA events on the index's stream)}. */
 int crs_index_set_option(crs_index* idx, const char* name, int64_t value);
+/* device time of the dominant kernel(s) (scan passes or GEMM) of the last search, from the
+ * CUDA events recorded when "profiling" is on; waits for that search to finish. */
+int crs_index_last_kernel_ms(crs_index* idx, float* out_ms);
 
 /* raw -> float similarity scale of this index: sim = raw * scale (1 for F16/BF16,
  * (a/127)^2 for I8, 1/dim for B1). */
