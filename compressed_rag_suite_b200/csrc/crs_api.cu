@@ -359,6 +359,10 @@ int crs_index_search(crs_index* ix, const void* queries, int nq, int k, float mi
     int lpl;
     if (is_float) { if (k <= 16) lpl = 1; else if (k <= 112) lpl = 4; else return fail(CRS_EINVAL, "k > 112 not supported for float stores"); }
     else { if (k <= 32) lpl = 1; else if (k <= 128) lpl = 4; else return fail(CRS_EINVAL, "k > 128 not supported"); }
+    // batches go to the tcgen05 contraction (K4); single queries / unsupported shapes stream-scan (K1)
+    const bool use_gemm = is_float && ix->force_path != 0 && crs::gemm_supported(ix->dim_padded, k) &&
+                          (ix->force_path == 1 || nq >= 8);
+    if (use_gemm) lpl = 1;
     const int M = 32 * lpl;
 
     std::lock_guard<std::mutex> lk(ix->mu);
@@ -416,7 +420,7 @@ int crs_index_search(crs_index* ix, const void* queries, int nq, int k, float mi
         CRS_CUDA(ix->flags.ensure((size_t)nq));
 
         crs::FinalizeArgs fa{};
-        fa.cand = ix->cand.p; fa.n_lists = n_lists; fa.lpl = lpl; fa.nq = nq; fa.k = k;
+        fa.cand = ix->cand.p; fa.n_lists = n_lists; fa.list_len = M; fa.lpl = lpl; fa.nq = nq; fa.k = k;
         fa.codes = ix->codes; fa.qcodes = ix->qcodes.p; fa.qnorms = ix->qnorms.p;
         fa.dim_padded = ix->dim_padded; fa.bf16 = ix->store == CRS_BF16;
         fa.row_norm_bound = ix->row_norm_bound;
@@ -437,11 +441,25 @@ int crs_index_search(crs_index* ix, const void* queries, int nq, int k, float mi
                 if (ix->metric == CRS_COSINE && min_similarity > -INFINITY)
                     tau_pre = min_similarity - eps_rel * 1.00390625f * ix->row_norm_bound;
                 if (ix->profiling) CRS_CUDA(cudaEventRecord(ix->ev0, st));
-                for (int q = 0; q < nq; ++q) {
-                    CRS_CUDA(crs::launch_scan_f16(st, ix->codes, ix->count, ix->dim_padded, fa.bf16,
-                                                  ix->qcodes.p + (size_t)q * ix->row_bytes, tau_pre,
-                                                  ix->cand.p + (size_t)q * n_lists * M, plan));
+                if (use_gemm) {
+                    // tensor-core accumulation may truncate instead of round: allow one ulp per term
+                    fa.eps_rel = (float)((double)ix->dim_padded * ldexp(1.0, -23) * 1.05 * ix->eps_scale);
+                    if (tau_pre > -INFINITY)
+                        tau_pre = min_similarity - fa.eps_rel * 1.00390625f * ix->row_norm_bound;
+                    int n_slices = 0;
+                    CRS_CUDA(crs::launch_gemm_topk(st, ix->codes, ix->count, ix->dim_padded, fa.bf16, ix->qcodes.p, nq, k,
+                                                   tau_pre, ix->cand.p, ix->num_sms, &n_slices));
                     ++launches;
+                    fa.n_lists = n_slices;
+                    fa.list_len = crs::gemm_list_len(k);
+                    ix->stats.path = 1; ix->stats.grid = n_slices * ((nq + 127) / 128); ix->stats.list_len = fa.list_len;
+                } else {
+                    for (int q = 0; q < nq; ++q) {
+                        CRS_CUDA(crs::launch_scan_f16(st, ix->codes, ix->count, ix->dim_padded, fa.bf16,
+                                                      ix->qcodes.p + (size_t)q * ix->row_bytes, tau_pre,
+                                                      ix->cand.p + (size_t)q * n_lists * M, plan));
+                        ++launches;
+                    }
                 }
                 if (ix->profiling) { CRS_CUDA(cudaEventRecord(ix->ev1, st)); ix->ev_valid = true; }
                 fa.mode = 0; fa.only_flagged = 0;
@@ -467,6 +485,7 @@ int crs_index_search(crs_index* ix, const void* queries, int nq, int k, float mi
                 CRS_CUDA(crs::launch_exact_scan(st, ix->codes, ix->count, ix->dim_padded, fa.bf16, ix->qcodes.p, nq,
                                                 ix->flags.p, min_similarity, ix->cand.p, plan));
                 fa.mode = 1; fa.only_flagged = 1;
+                fa.n_lists = n_lists; fa.list_len = M;      // the exact scan writes one full list per CTA
                 CRS_CUDA(crs::launch_finalize(st, fa));
                 launches += 2;
             }

@@ -32,6 +32,8 @@ cudaError_t launch_scan_b1(cudaStream_t st, const void* codes, int64_t n, int di
 struct FinalizeArgs {
     const uint64_t* cand;      // [nq][n_lists][M] sorted lists
     int n_lists;
+    int list_len;              // valid entries per list (<= M = 32*lpl); a list whose last valid slot is
+                               // occupied was cut there, and its cut score bounds everything it dropped
     int lpl;
     int nq;
     int k;
@@ -60,6 +62,15 @@ cudaError_t launch_finalize(cudaStream_t st, const FinalizeArgs& a);
 cudaError_t launch_exact_scan(cudaStream_t st, const void* codes, int64_t n, int dim_padded, bool bf16,
                               const void* qcodes, int nq, const int32_t* flags, float min_similarity,
                               uint64_t* cand, const ScanPlan& plan);
+
+// K4: tcgen05 Q*C^T with fused top-L epilogue (fp16 / bf16 stores, Dp <= 384, k <= 24).
+// Writes one sorted list of gemm_list_len(k) keys per (query, corpus slice), list stride 32;
+// *n_slices_out = number of lists per query.
+bool gemm_supported(int dim_padded, int k);
+int gemm_list_len(int k);
+cudaError_t launch_gemm_topk(cudaStream_t st, const void* codes, int64_t n, int dim_padded, bool bf16,
+                             const void* qcodes, int nq, int k, float tau_pre, uint64_t* cand, int num_sms,
+                             int* n_slices_out);
 
 // K7: merge G lists of k_in (id, raw score) per query into the global top k_out.
 cudaError_t launch_merge_topk(cudaStream_t st, const uint32_t* ids, const void* scores, int is_int,

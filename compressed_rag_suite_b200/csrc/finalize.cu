@@ -59,6 +59,7 @@ finalize_kernel(FinalizeArgs a) {
     __shared__ uint64_t stage[kFinalizeWarps * M];
     __shared__ uint64_t fast_keys[M];
     __shared__ uint64_t exact_keys[M];
+    __shared__ uint64_t cut_stage[kFinalizeWarps];
     const int q = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (a.only_flagged && a.flags[q] == 0) return;
@@ -68,12 +69,15 @@ finalize_kernel(FinalizeArgs a) {
 #pragma unroll
     for (int s = 0; s < LPL; ++s) e[s] = 0ull;
     const uint64_t* base = a.cand + (size_t)q * a.n_lists * M;
+    uint64_t cut = 0ull;        // largest key at which any input list was cut (0 = no list was full)
     for (int l = warp; l < a.n_lists; l += kFinalizeWarps) {
         uint64_t b[LPL];
 #pragma unroll
         for (int s = 0; s < LPL; ++s) b[s] = base[(size_t)l * M + lane * LPL + s];
+        cut = u64max(cut, base[(size_t)l * M + a.list_len - 1]);
         warp_merge_desc<LPL>(e, b, lane);
     }
+    if (lane == 0) cut_stage[warp] = cut;
     block_merge_lists<LPL, kFinalizeWarps>(e, stage, warp, lane);
     if (warp == 0) {
 #pragma unroll
@@ -116,7 +120,12 @@ finalize_kernel(FinalizeArgs a) {
     const int count = min(nvalid, a.k);
 
     if (a.mode == 0) {
-        const uint64_t last_fast = fast_keys[M - 1];          // M-th candidate by fast score (0 = list not full)
+        // everything dropped before this point scored (fast) no more than the largest cut:
+        // the M-th merged candidate when the merged list is full, or the last entry of any
+        // input list that was full
+        uint64_t last_fast = fast_keys[M - 1];
+#pragma unroll
+        for (int w = 0; w < kFinalizeWarps; ++w) last_fast = u64max(last_fast, cut_stage[w]);
         bool certified = true;
         if (last_fast != 0ull) {
             const float a_min = unorderable_f32(key_ord(last_fast));

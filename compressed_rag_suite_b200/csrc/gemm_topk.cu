@@ -1,0 +1,312 @@
+// K4 — batched search as a dense contraction S = Q * C^T on the tcgen05 tensor cores
+// with a fused threshold + top-L epilogue: the score matrix never reaches HBM.
+//
+// Replaces, for a whole batch of queries, the distance pass `collection.query` performs
+// inside ChromaDB (reference rag/indexing.py:171-176; the reference itself can only ask
+// one query at a time).  FLOPs per launch: 2 * nq_padded * n_rows * Dp.
+//
+// Work split: CTA = (query tile of 128 queries, contiguous slice of corpus tiles).
+// blockIdx = slice * n_qtiles + qtile, so the CTAs that stream the same corpus slice are
+// launched next to each other and share it through L2.
+//
+// Roles inside a CTA (192 threads, 1 CTA / SM):
+//   warp 0  TMA producer : loads the CTA's query tile once (A operand, stays resident in
+//           smem: KCH chunks of [128 x 64] fp16, SWIZZLE_128B), then streams corpus tiles
+//           as [256 rows x 64 k] chunks (B operand) through a STAGES-deep mbarrier ring.
+//   warp 1  MMA issuer   : one elected lane issues tcgen05.mma.cta_group::1.kind::f16
+//           (M=128, N=256, K=16) 4 per chunk, KCH chunks per corpus tile, accumulating
+//           in TMEM; tcgen05.commit frees the smem slot / publishes the accumulator.
+//           Accumulators are double-buffered (2 x 256 TMEM columns).
+//   warps 2-5 epilogue   : TMEM lane = query, column = corpus row.  Each thread reads its
+//           query's 256 scores in 32-column slabs (tcgen05.ld.32x32b.x32), tests the slab
+//           maximum against its running threshold (the L-th best so far), and only on a
+//           hit walks the slab and inserts into a sorted register list of L keys.
+// At the end every thread writes its sorted list: cand[q][slice][0..L) (stride M = 32).
+// finalize.cu merges the slices' lists, rescores the candidates exactly in fp64,
+// certifies the top-k and falls back to the exhaustive fp64 pass when it cannot.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "crs_internal.h"
+
+namespace crs {
+
+constexpr int kGemmThreads = 192;
+constexpr int kTileQ = 128;        // UMMA M
+constexpr int kTileC = 256;        // UMMA N (corpus rows per tile)
+constexpr int kChunkK = 64;        // fp16 elements per 128-byte swizzle row
+constexpr int kStages = 4;
+constexpr int kAChunkBytes = kTileQ * kChunkK * 2;     // 16 KB
+constexpr int kBStageBytes = kTileC * kChunkK * 2;     // 32 KB
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_512(uint32_t* smem_slot) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(smem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_512(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor: rows of 128 bytes, 8-row groups
+// 1024 bytes apart (SBO), descriptor version 1 (Blackwell).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+
+// sorted (descending) register list of L keys; insert keeps the L largest
+template <int L>
+__device__ __forceinline__ void list_insert(uint64_t (&a)[L], uint64_t x) {
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+        const uint64_t hi = u64max(a[i], x);
+        x = u64min(a[i], x);
+        a[i] = hi;
+    }
+}
+
+template <int KCH, int L>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
+                 int64_t n_rows, int n_qtiles, int n_slices, uint32_t idesc, float tau_pre,
+                 uint64_t* __restrict__ cand, int nq, int list_stride) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t full_bar[kStages], empty_bar[kStages], a_bar, tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_base_slot;
+
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;                                   // KCH x 16 KB
+    uint8_t* smem_b = smem + KCH * kAChunkBytes;              // kStages x 32 KB
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qtile = blockIdx.x % n_qtiles;
+    const int slice = blockIdx.x / n_qtiles;
+    const int64_t tiles_total = (n_rows + kTileC - 1) / kTileC;
+    const int64_t tile_lo = tiles_total * slice / n_slices;
+    const int64_t tile_hi = tiles_total * (slice + 1) / n_slices;
+    const int n_tiles = (int)(tile_hi - tile_lo);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&a_bar, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc_512(&tmem_base_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&a_bar, KCH * kAChunkBytes);
+            for (int kc = 0; kc < KCH; ++kc)
+                tma_load_2d(smem_a + kc * kAChunkBytes, &map_q, kc * kChunkK, qtile * kTileQ, &a_bar);
+            int stage = 0; uint32_t phase = 0;
+            for (int t = 0; t < n_tiles; ++t) {
+                const int row0 = (int)((tile_lo + t) * kTileC);
+                for (int kc = 0; kc < KCH; ++kc) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], kBStageBytes);
+                    tma_load_2d(smem_b + stage * kBStageBytes, &map_c, kc * kChunkK, row0, &full_bar[stage]);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            mbar_wait(&a_bar, 0);
+            tc_fence_after();
+            int stage = 0; uint32_t phase = 0;
+            for (int t = 0; t < n_tiles; ++t) {
+                const int buf = t & 1;
+                const uint32_t tphase = (t >> 1) & 1;
+                mbar_wait(&tempty_bar[buf], tphase ^ 1);            // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * kTileC;
+                for (int kc = 0; kc < KCH; ++kc) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t a_desc = make_smem_desc(smem_u32(smem_a + kc * kAChunkBytes));
+                    const uint64_t b_desc = make_smem_desc(smem_u32(smem_b + stage * kBStageBytes));
+#pragma unroll
+                    for (int k = 0; k < kChunkK / 16; ++k)          // +32 bytes per K=16 step inside the swizzle row
+                        umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kc | k) != 0);
+                    umma_commit(&empty_bar[stage]);                 // smem slot reusable once these MMAs retire
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull_bar[buf]);                       // accumulator complete
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue (warps 2..5)
+        const int lane_grp = warp & 3;                              // TMEM lanes this warp may touch
+        const int qrow = lane_grp * 32 + lane;
+        const int q = qtile * kTileQ + qrow;
+        uint64_t best[L];
+#pragma unroll
+        for (int i = 0; i < L; ++i) best[i] = 0ull;
+        float tau = tau_pre;                                        // running threshold: L-th best so far
+        for (int t = 0; t < n_tiles; ++t) {
+            const int buf = t & 1;
+            const uint32_t tphase = (t >> 1) & 1;
+            mbar_wait(&tfull_bar[buf], tphase);
+            tc_fence_after();
+            const int64_t row0 = (tile_lo + t) * kTileC;
+            const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + buf * kTileC;
+#pragma unroll 1
+            for (int slab = 0; slab < kTileC / 32; ++slab) {
+                uint32_t r[32];
+                tmem_ld32(taddr + slab * 32, r);
+                tmem_ld_wait();
+                float m = __uint_as_float(r[0]);
+#pragma unroll
+                for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(r[i]));
+                if (m >= tau) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float v = __uint_as_float(r[i]);
+                        const int64_t row = row0 + slab * 32 + i;
+                        if (v >= tau && row < n_rows) {
+                            const uint64_t key = make_key(orderable_f32(v), (uint32_t)row);
+                            if (key > best[L - 1]) {
+                                list_insert<L>(best, key);
+                                if (best[L - 1] != 0ull) tau = fmaxf(tau_pre, unorderable_f32(key_ord(best[L - 1])));
+                            }
+                        }
+                    }
+                }
+                __syncwarp();                                       // tcgen05.ld is .aligned: reconverge first
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        }
+        if (q < nq) {
+            uint64_t* dst = cand + ((size_t)q * n_slices + slice) * list_stride;
+#pragma unroll
+            for (int i = 0; i < L; ++i) dst[i] = best[i];
+            for (int i = L; i < list_stride; ++i) dst[i] = 0ull;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc_512(tmem_base);
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+static bool make_map(CUtensorMap* map, const void* base, int64_t rows, int dim_padded, int box_rows, bool bf16) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t gdim[2] = {(cuuint64_t)dim_padded, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)dim_padded * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kChunkK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+              const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int KCH, int L>
+static cudaError_t launch_kch(cudaStream_t st, const CUtensorMap& mq, const CUtensorMap& mc, int64_t n, int n_qtiles,
+                              int n_slices, uint32_t idesc, float tau_pre, uint64_t* cand, int nq, int list_stride) {
+    const size_t smem = (size_t)KCH * kAChunkBytes + (size_t)kStages * kBStageBytes + 1024;
+    auto kern = gemm_topk_kernel<KCH, L>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<n_qtiles * n_slices, kGemmThreads, smem, st>>>(mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq,
+                                                          list_stride);
+    return cudaGetLastError();
+}
+
+bool gemm_supported(int dim_padded, int k) {
+    const int kch = dim_padded / kChunkK;
+    return (kch >= 1 && kch <= 6) && k <= 24;
+}
+
+int gemm_list_len(int k) { return k <= 10 ? 16 : 32; }
+
+cudaError_t launch_gemm_topk(cudaStream_t st, const void* codes, int64_t n, int dim_padded, bool bf16,
+                             const void* qcodes, int nq, int k, float tau_pre, uint64_t* cand, int num_sms,
+                             int* n_slices_out) {
+    const int kch = dim_padded / kChunkK;
+    const int n_qtiles = (nq + kTileQ - 1) / kTileQ;
+    int n_slices = num_sms / n_qtiles;
+    if (n_slices < 1) n_slices = 1;
+    const int64_t tiles_total = (n + kTileC - 1) / kTileC;
+    if (n_slices > tiles_total) n_slices = (int)tiles_total;
+    *n_slices_out = n_slices;
+    CUtensorMap mq, mc;
+    if (!make_map(&mq, qcodes, nq, dim_padded, kTileQ, bf16) || !make_map(&mc, codes, n, dim_padded, kTileC, bf16))
+        return cudaErrorInvalidValue;
+    // instruction descriptor: D=f32, A=B=f16|bf16, both K-major, N=256, M=128
+    const uint32_t fmt = bf16 ? 1u : 0u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kTileC >> 3) << 17) | ((uint32_t)(kTileQ >> 4) << 24);
+    const int L = gemm_list_len(k);
+#define CRS_GEMM_CASE(KCH_)                                                                                         \
+    case KCH_:                                                                                                      \
+        return L == 16 ? launch_kch<KCH_, 16>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32)       \
+                       : launch_kch<KCH_, 32>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32);
+    switch (kch) {
+        CRS_GEMM_CASE(1)
+        CRS_GEMM_CASE(2)
+        CRS_GEMM_CASE(3)
+        CRS_GEMM_CASE(4)
+        CRS_GEMM_CASE(6)
+        default: return cudaErrorInvalidValue;
+    }
+#undef CRS_GEMM_CASE
+}
+
+}  // namespace crs

