@@ -96,6 +96,7 @@ struct crs_index {
     // options
     int force_path = -1;
     int force_exact = 0;
+    int gemm_cluster = 0;
     double eps_scale = 1.0;
     // scratch
     DevScratch<float> qsrc, qnorms, norms_tmp;
@@ -246,6 +247,7 @@ int crs_index_set_option(crs_index* ix, const char* name, int64_t value) {
     std::lock_guard<std::mutex> lk(ix->mu);
     if (!strcmp(name, "force_path")) ix->force_path = (int)value;
     else if (!strcmp(name, "force_exact")) ix->force_exact = (int)value;
+    else if (!strcmp(name, "gemm_cluster")) ix->gemm_cluster = (int)value;
     else if (!strcmp(name, "eps_scale")) ix->eps_scale = (double)value / 1000.0;
     else if (!strcmp(name, "profiling")) {
         DeviceGuard g(ix->device);
@@ -448,7 +450,7 @@ int crs_index_search(crs_index* ix, const void* queries, int nq, int k, float mi
                         tau_pre = min_similarity - fa.eps_rel * 1.00390625f * ix->row_norm_bound;
                     int n_slices = 0;
                     CRS_CUDA(crs::launch_gemm_topk(st, ix->codes, ix->count, ix->dim_padded, fa.bf16, ix->qcodes.p, nq, k,
-                                                   tau_pre, ix->cand.p, ix->num_sms, &n_slices));
+                                                   tau_pre, ix->cand.p, ix->num_sms, ix->gemm_cluster, &n_slices));
                     ++launches;
                     fa.n_lists = n_slices;
                     fa.list_len = crs::gemm_list_len(k);

@@ -70,7 +70,7 @@ bool gemm_supported(int dim_padded, int k);
 int gemm_list_len(int k);
 cudaError_t launch_gemm_topk(cudaStream_t st, const void* codes, int64_t n, int dim_padded, bool bf16,
                              const void* qcodes, int nq, int k, float tau_pre, uint64_t* cand, int num_sms,
-                             int* n_slices_out);
+                             int cluster /*0 = auto, else 1|2|4 query tiles per multicast cluster*/, int* n_slices_out);
 
 // K7: merge G lists of k_in (id, raw score) per query into the global top k_out.
 cudaError_t launch_merge_topk(cudaStream_t st, const uint32_t* ids, const void* scores, int is_int,

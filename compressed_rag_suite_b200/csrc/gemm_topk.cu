@@ -45,6 +45,24 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// multicast variant: the box lands at the same smem offset in every CTA of `mask`, and each of
+// those CTAs' mbarrier (same offset) receives the complete_tx
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar,
+                                               uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_alloc_512(uint32_t* smem_slot) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(smem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -63,6 +81,11 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrive on the barrier at this offset in every CTA of `mask` once the MMAs issued so far retire
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -95,7 +118,47 @@ __device__ __forceinline__ void list_insert(uint64_t (&a)[L], uint64_t x) {
     }
 }
 
-template <int KCH, int L>
+// One thread's 32 scores (consecutive corpus rows row0..row0+31 of its query).  Fast path:
+// tree max against the running threshold.  Slow path (rare once the list is warm): a hit mask
+// and ONE copy of the insert code, walked only over this thread's own hits, so a warp runs
+// max-over-lanes(hits) insert bodies instead of one per column any lane hit.
+template <int L>
+__device__ __forceinline__ void slab_scan(const uint32_t (&r)[32], int64_t row0, int64_t n_rows, float tau_pre,
+                                          float& tau, uint64_t (&best)[L]) {
+    float m[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) m[i] = fmaxf(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+#pragma unroll
+    for (int w = 8; w >= 1; w >>= 1) {
+#pragma unroll
+        for (int i = 0; i < w; ++i) m[i] = fmaxf(m[i], m[i + w]);
+    }
+    if (m[0] >= tau) {
+        unsigned mask = 0;
+        float tmp[32];                       // dynamically indexed -> local memory, touched on this path only
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const float v = __uint_as_float(r[i]);
+            tmp[i] = v;
+            mask |= (v >= tau) ? (1u << i) : 0u;
+        }
+        while (mask) {
+            const int i = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float v = tmp[i];
+            const int64_t row = row0 + i;
+            if (v >= tau && row < n_rows) {
+                const uint64_t key = make_key(orderable_f32(v), (uint32_t)row);
+                if (key > best[L - 1]) {
+                    list_insert<L>(best, key);
+                    if (best[L - 1] != 0ull) tau = fmaxf(tau_pre, unorderable_f32(key_ord(best[L - 1])));
+                }
+            }
+        }
+    }
+}
+
+template <int KCH, int L, int CS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
                  int64_t n_rows, int n_qtiles, int n_slices, uint32_t idesc, float tau_pre,
@@ -109,15 +172,21 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     uint8_t* smem_b = smem + KCH * kAChunkBytes;              // kStages x 32 KB
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qtile = blockIdx.x % n_qtiles;
-    const int slice = blockIdx.x / n_qtiles;
+    // a cluster = CS query tiles working on the same corpus slice; its CTAs split every corpus
+    // chunk CS ways and multicast the pieces to each other (one L2 read feeds CS SMs)
+    const int crank = (CS > 1) ? (int)cluster_ctarank() : 0;
+    const int cluster_id = blockIdx.x / CS;
+    const int qgroups = n_qtiles / CS;                      // n_qtiles is a multiple of CS
+    const int qtile = (cluster_id % qgroups) * CS + crank;
+    const int slice = cluster_id / qgroups;
+    constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1);
     const int64_t tiles_total = (n_rows + kTileC - 1) / kTileC;
     const int64_t tile_lo = tiles_total * slice / n_slices;
     const int64_t tile_hi = tiles_total * (slice + 1) / n_slices;
     const int n_tiles = (int)(tile_hi - tile_lo);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CS); }
         mbar_init(&a_bar, 1);
         for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
         fence_mbar_init();
@@ -125,6 +194,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     if (warp == 1) tmem_alloc_512(&tmem_base_slot);
     tc_fence_before();
     __syncthreads();
+    if constexpr (CS > 1) cluster_sync_all();               // peers' barriers exist before anything is multicast
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
 
@@ -139,8 +209,14 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 const int row0 = (int)((tile_lo + t) * kTileC);
                 for (int kc = 0; kc < KCH; ++kc) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], kBStageBytes);
-                    tma_load_2d(smem_b + stage * kBStageBytes, &map_c, kc * kChunkK, row0, &full_bar[stage]);
+                    mbar_arrive_expect_tx(&full_bar[stage], kBStageBytes);      // all CS pieces land here
+                    if constexpr (CS == 1) {
+                        tma_load_2d(smem_b + stage * kBStageBytes, &map_c, kc * kChunkK, row0, &full_bar[stage]);
+                    } else {
+                        constexpr int kPieceRows = kTileC / CS;
+                        tma_load_2d_mc(smem_b + stage * kBStageBytes + crank * kPieceRows * 128, &map_c, kc * kChunkK,
+                                       row0 + crank * kPieceRows, &full_bar[stage], kMask);
+                    }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -165,7 +241,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 #pragma unroll
                     for (int k = 0; k < kChunkK / 16; ++k)          // +32 bytes per K=16 step inside the swizzle row
                         umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kc | k) != 0);
-                    umma_commit(&empty_bar[stage]);                 // smem slot reusable once these MMAs retire
+                    if constexpr (CS == 1) umma_commit(&empty_bar[stage]);   // slot reusable once these MMAs retire
+                    else umma_commit_mc(&empty_bar[stage], kMask);          // ... in every CTA that writes into it
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&tfull_bar[buf]);                       // accumulator complete
@@ -179,7 +256,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         uint64_t best[L];
 #pragma unroll
         for (int i = 0; i < L; ++i) best[i] = 0ull;
-        float tau = tau_pre;                                        // running threshold: L-th best so far
+        // running threshold: L-th best so far.  Padding rows of the last query tile (all-zero
+        // queries, every score 0) must never enter the slow path: their threshold is +inf.
+        float tau = (q < nq) ? tau_pre : INFINITY;
         for (int t = 0; t < n_tiles; ++t) {
             const int buf = t & 1;
             const uint32_t tphase = (t >> 1) & 1;
@@ -187,29 +266,20 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             tc_fence_after();
             const int64_t row0 = (tile_lo + t) * kTileC;
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + buf * kTileC;
+            // two register slabs in flight: the TMEM load of slab s+1 overlaps the scan of slab s
+            uint32_t ra[32], rb[32];
+            tmem_ld32(taddr, ra);
+            tmem_ld_wait();
 #pragma unroll 1
-            for (int slab = 0; slab < kTileC / 32; ++slab) {
-                uint32_t r[32];
-                tmem_ld32(taddr + slab * 32, r);
+            for (int slab = 0; slab < kTileC / 32; slab += 2) {
+                tmem_ld32(taddr + (slab + 1) * 32, rb);
+                slab_scan<L>(ra, row0 + slab * 32, n_rows, tau_pre, tau, best);
+                __syncwarp();                                       // tcgen05.ld / wait are .aligned: reconverge first
                 tmem_ld_wait();
-                float m = __uint_as_float(r[0]);
-#pragma unroll
-                for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(r[i]));
-                if (m >= tau) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float v = __uint_as_float(r[i]);
-                        const int64_t row = row0 + slab * 32 + i;
-                        if (v >= tau && row < n_rows) {
-                            const uint64_t key = make_key(orderable_f32(v), (uint32_t)row);
-                            if (key > best[L - 1]) {
-                                list_insert<L>(best, key);
-                                if (best[L - 1] != 0ull) tau = fmaxf(tau_pre, unorderable_f32(key_ord(best[L - 1])));
-                            }
-                        }
-                    }
-                }
-                __syncwarp();                                       // tcgen05.ld is .aligned: reconverge first
+                if (slab + 2 < kTileC / 32) tmem_ld32(taddr + (slab + 2) * 32, ra);
+                slab_scan<L>(rb, row0 + (slab + 1) * 32, n_rows, tau_pre, tau, best);
+                __syncwarp();
+                tmem_ld_wait();
             }
             tc_fence_before();
             __syncwarp();
@@ -225,6 +295,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 
     tc_fence_before();
     __syncthreads();
+    if constexpr (CS > 1) cluster_sync_all();               // no CTA leaves while peers may still signal it
     if (warp == 1) tmem_dealloc_512(tmem_base);
 }
 
@@ -258,16 +329,34 @@ static bool make_map(CUtensorMap* map, const void* base, int64_t rows, int dim_p
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int KCH, int L>
+template <int KCH, int L, int CS>
 static cudaError_t launch_kch(cudaStream_t st, const CUtensorMap& mq, const CUtensorMap& mc, int64_t n, int n_qtiles,
                               int n_slices, uint32_t idesc, float tau_pre, uint64_t* cand, int nq, int list_stride) {
     const size_t smem = (size_t)KCH * kAChunkBytes + (size_t)kStages * kBStageBytes + 1024;
-    auto kern = gemm_topk_kernel<KCH, L>;
+    auto kern = gemm_topk_kernel<KCH, L, CS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<n_qtiles * n_slices, kGemmThreads, smem, st>>>(mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq,
-                                                          list_stride);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(n_qtiles * n_slices));
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, list_stride);
+}
+
+template <int KCH, int L>
+static cudaError_t launch_cs(int cs, cudaStream_t st, const CUtensorMap& mq, const CUtensorMap& mc, int64_t n,
+                             int n_qtiles, int n_slices, uint32_t idesc, float tau_pre, uint64_t* cand, int nq) {
+    if (cs == 4) return launch_kch<KCH, L, 4>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32);
+    if (cs == 2) return launch_kch<KCH, L, 2>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32);
+    return launch_kch<KCH, L, 1>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32);
 }
 
 bool gemm_supported(int dim_padded, int k) {
@@ -279,16 +368,21 @@ int gemm_list_len(int k) { return k <= 10 ? 16 : 32; }
 
 cudaError_t launch_gemm_topk(cudaStream_t st, const void* codes, int64_t n, int dim_padded, bool bf16,
                              const void* qcodes, int nq, int k, float tau_pre, uint64_t* cand, int num_sms,
-                             int* n_slices_out) {
+                             int cluster, int* n_slices_out) {
     const int kch = dim_padded / kChunkK;
-    const int n_qtiles = (nq + kTileQ - 1) / kTileQ;
+    int n_qtiles = (nq + kTileQ - 1) / kTileQ;
+    // cluster size: query tiles that share one corpus stream through TMA multicast
+    int cs = cluster > 0 ? cluster : (n_qtiles >= 2 ? 2 : 1);
+    if (cs != 1 && cs != 2 && cs != 4) cs = 1;
+    while (cs > 1 && n_qtiles < cs) cs >>= 1;
+    n_qtiles = (n_qtiles + cs - 1) / cs * cs;              // padded query tiles are all-zero (TMA OOB fill)
     int n_slices = num_sms / n_qtiles;
     if (n_slices < 1) n_slices = 1;
     const int64_t tiles_total = (n + kTileC - 1) / kTileC;
     if (n_slices > tiles_total) n_slices = (int)tiles_total;
     *n_slices_out = n_slices;
     CUtensorMap mq, mc;
-    if (!make_map(&mq, qcodes, nq, dim_padded, kTileQ, bf16) || !make_map(&mc, codes, n, dim_padded, kTileC, bf16))
+    if (!make_map(&mq, qcodes, nq, dim_padded, kTileQ, bf16) || !make_map(&mc, codes, n, dim_padded, kTileC / cs, bf16))
         return cudaErrorInvalidValue;
     // instruction descriptor: D=f32, A=B=f16|bf16, both K-major, N=256, M=128
     const uint32_t fmt = bf16 ? 1u : 0u;
@@ -296,8 +390,8 @@ cudaError_t launch_gemm_topk(cudaStream_t st, const void* codes, int64_t n, int 
     const int L = gemm_list_len(k);
 #define CRS_GEMM_CASE(KCH_)                                                                                         \
     case KCH_:                                                                                                      \
-        return L == 16 ? launch_kch<KCH_, 16>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32)       \
-                       : launch_kch<KCH_, 32>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32);
+        return L == 16 ? launch_cs<KCH_, 16>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq)        \
+                       : launch_cs<KCH_, 32>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq);
     switch (kch) {
         CRS_GEMM_CASE(1)
         CRS_GEMM_CASE(2)

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from compressed_rag_suite_b200.index import ShardIndex
 
-def run(n, dim, nq, k, iters=10, store="f16"):
+def run(n, dim, nq, k, iters=10, store="f16", cluster=0):
     ix = ShardIndex(dim, dtype=store, reserve_rows=n)
     g = torch.Generator(device="cuda"); g.manual_seed(0)
     cen = torch.randn(4096, dim, device="cuda", generator=g); cen /= cen.norm(dim=1, keepdim=True)
@@ -17,6 +17,7 @@ def run(n, dim, nq, k, iters=10, store="f16"):
     z = torch.randn(nq, dim, device="cuda", generator=g); z /= z.norm(dim=1, keepdim=True)
     q = 0.6 * cen[torch.randint(0, 4096, (nq,), device="cuda", generator=g)] + 0.8 * z
     ix.set_option("profiling", 1)
+    ix.set_option("gemm_cluster", cluster)
     for _ in range(3):
         ix.search(q, k)
     torch.cuda.synchronize()
@@ -28,15 +29,16 @@ def run(n, dim, nq, k, iters=10, store="f16"):
     ts.sort(); ks.sort()
     st = ix.last_stats()
     flops = 2.0 * ((nq + 127) // 128 * 128) * n * ix.dim_padded
-    print(json.dumps({"n": n, "dim": dim, "nq": nq, "k": k, "path": st["path"], "ms_med": round(ts[len(ts)//2], 3),
+    print(json.dumps({"cluster": cluster, "n": n, "dim": dim, "nq": nq, "k": k, "path": st["path"], "ms_med": round(ts[len(ts)//2], 3),
                       "kernel_ms_med": round(ks[len(ks)//2], 3), "qps": round(nq / ts[len(ts)//2] * 1e3),
                       "TFLOPs_kernel": round(flops / ks[len(ks)//2] / 1e9, 1), "GBps_kernel": round(n * ix.row_bytes / ks[len(ks)//2] / 1e6, 1),
                       "launches": st["kernel_launches"], "grid": st["grid"], "uncert": st["uncertified_total"]}), flush=True)
     ix.close()
 
 if __name__ == "__main__":
-    run(1_000_000, 384, 1024, 10)
-    run(10_000_000, 384, 1024, 10)
+    for cs in (1, 2, 4):
+        run(1_000_000, 384, 1024, 10, cluster=cs)
+        run(10_000_000, 384, 1024, 10, cluster=cs)
     run(10_000_000, 384, 128, 10)
+    run(10_000_000, 384, 256, 10, cluster=2)
     run(10_000_000, 384, 16, 10)
-    run(4_000_000, 384, 1024, 10, store="bf16")
