@@ -147,15 +147,19 @@ class ClockSampler(threading.Thread):
                 out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
-                    self.samples.append([c.strip() for c in out.split(",")])
+                    self.samples.append((time.perf_counter(), [c.strip() for c in out.split(",")]))
             except Exception:
                 pass
             time.sleep(0.05)
 
-    def summary(self):
+    def summary(self, t0, t1):
+        """Median SM clock / throttle reasons over the samples taken while the GPU was under the
+        bench load (t0..t1, perf_counter seconds)."""
         sm, reasons, mx = [], set(), None
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        for ts, s in self.samples:
+            if ts < t0 or ts > t1:
+                continue
             try:
                 sm.append(float(s[1]))
                 mx = float(s[2])
@@ -245,21 +249,31 @@ def run_ours(a):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        t_wait = time.perf_counter()
+        while not sampler.samples and time.perf_counter() - t_wait < 10.0:
+            time.sleep(0.02)                                     # first nvidia-smi call is slow: get it out of the way
     warm = max(a.warmup, 3)
+    t_load0 = time.perf_counter()
     ms_total, wall_total = timed(step_device, a.steps, warm)
-    # dominant-kernel time: a few extra profiled steps (events on the library's stream)
-    kms = []
-    for _ in range(min(a.steps, 5)):
-        step_device()
-        kms.append(ix.last_kernel_ms())
+    # dominant-kernel time of the timed steps: the library brackets it with CUDA events on its
+    # launch stream and keeps the last 32 pairs, so nothing synchronises inside the timed loop
+    kms = ix.kernel_ms_history()[-a.steps:]
     stats = ix.last_stats()
     e2e_total, _ = timed(step_e2e, a.steps, 1)
+    # keep the same load running until nvidia-smi has sampled it a few times (the timed
+    # regions above are shorter than one nvidia-smi call)
+    t_probe = time.perf_counter()
+    while time.perf_counter() - t_probe < 2.0:
+        step_device()
+        torch.cuda.synchronize()
+    barrier()
+    t_load1 = time.perf_counter()
     sampler.stop_flag = True
 
     ms_step = ms_total / a.steps
     qps = a.batch / (ms_step * 1e-3)
     e2e_qps = a.batch / (e2e_total / a.steps * 1e-3)
-    kernel_ms = sorted(kms)[len(kms) // 2]
+    kernel_ms = sum(kms) / len(kms)          # average launch duration over the timed steps
     kt = torch.tensor([kernel_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(kt, op=dist.ReduceOp.MAX)
@@ -318,7 +332,7 @@ def run_ours(a):
         "uncertified_queries_total": stats["uncertified_total"],
         "wall_ms_per_step": wall_total / a.steps,
         "roofline": roof,
-        "clocks": sampler.summary(),
+        "clocks": sampler.summary(t_load0, t_load1),
     }
     if world == 1 and not a.no_cpu_baseline:
         from oracle import cpu_baseline as cb

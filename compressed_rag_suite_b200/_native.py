@@ -38,6 +38,7 @@ SYMBOLS = {
     "crs_index_last_stats": (C.c_int, [_P, _P]),
     "crs_index_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "crs_index_last_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "crs_index_kernel_ms_history": (C.c_int, [_P, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]),
     "crs_index_similarity_scale": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "crs_index_fetch_rows": (C.c_int, [_P, _P, C.c_int, _P]),
     "crs_mmr": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_double, _P]),

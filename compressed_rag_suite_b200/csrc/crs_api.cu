@@ -108,8 +108,8 @@ struct crs_index {
     int32_t* n_flagged = nullptr;      // device counters: [0] this search, [1] since create
     crs_search_stats stats{};
     int profiling = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // bracket the dominant kernel(s) of the last search
-    bool ev_valid = false;
+    cudaEvent_t evs[32][2] = {};               // ring of event pairs bracketing the dominant kernel(s) of each search
+    int64_t ev_count = 0;                      // searches timed so far
     std::mutex mu;
 };
 
@@ -225,8 +225,7 @@ int crs_index_destroy(crs_index* ix) {
         cudaStreamSynchronize(ix->stream);
         if (ix->codes) cudaFree(ix->codes);
         if (ix->n_flagged) cudaFree(ix->n_flagged);
-        if (ix->ev0) cudaEventDestroy(ix->ev0);
-        if (ix->ev1) cudaEventDestroy(ix->ev1);
+        for (auto& p : ix->evs) { if (p[0]) cudaEventDestroy(p[0]); if (p[1]) cudaEventDestroy(p[1]); }
         ix->qsrc.release(); ix->qnorms.release(); ix->norms_tmp.release(); ix->qcodes.release();
         ix->stage_rows.release(); ix->cand.release(); ix->flags.release(); ix->counts_dev.release();
         ix->ids_dev.release(); ix->scores_dev.release();
@@ -252,9 +251,8 @@ int crs_index_set_option(crs_index* ix, const char* name, int64_t value) {
     else if (!strcmp(name, "profiling")) {
         DeviceGuard g(ix->device);
         ix->profiling = (int)value;
-        if (ix->profiling && !ix->ev0) {
-            CRS_CUDA(cudaEventCreate(&ix->ev0));
-            CRS_CUDA(cudaEventCreate(&ix->ev1));
+        if (ix->profiling && !ix->evs[0][0]) {
+            for (auto& p : ix->evs) { CRS_CUDA(cudaEventCreate(&p[0])); CRS_CUDA(cudaEventCreate(&p[1])); }
         }
     }
     else return fail(CRS_EINVAL, std::string("unknown option ") + name);
@@ -342,10 +340,28 @@ int crs_index_last_stats(const crs_index* ix, crs_search_stats* out) {
 int crs_index_last_kernel_ms(crs_index* ix, float* out_ms) {
     if (!ix || !out_ms) return fail(CRS_EINVAL, "bad argument");
     std::lock_guard<std::mutex> lk(ix->mu);
-    if (!ix->profiling || !ix->ev_valid) return fail(CRS_ESTATE, "profiling is off or no search was timed");
+    if (!ix->profiling || ix->ev_count == 0) return fail(CRS_ESTATE, "profiling is off or no search was timed");
     DeviceGuard g(ix->device);
-    CRS_CUDA(cudaEventSynchronize(ix->ev1));
-    CRS_CUDA(cudaEventElapsedTime(out_ms, ix->ev0, ix->ev1));
+    cudaEvent_t* p = ix->evs[(ix->ev_count - 1) % 32];
+    CRS_CUDA(cudaEventSynchronize(p[1]));
+    CRS_CUDA(cudaEventElapsedTime(out_ms, p[0], p[1]));
+    return CRS_OK;
+}
+
+int crs_index_kernel_ms_history(crs_index* ix, float* out_ms, int max_n, int* n_out) {
+    if (!ix || !out_ms || !n_out || max_n < 0) return fail(CRS_EINVAL, "bad argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    *n_out = 0;
+    if (!ix->profiling) return fail(CRS_ESTATE, "profiling is off");
+    DeviceGuard g(ix->device);
+    const int64_t have = std::min<int64_t>(ix->ev_count, 32);
+    const int n = (int)std::min<int64_t>(have, max_n);
+    for (int i = 0; i < n; ++i) {                          // oldest of the last n first
+        cudaEvent_t* p = ix->evs[(ix->ev_count - n + i) % 32];
+        CRS_CUDA(cudaEventSynchronize(p[1]));
+        CRS_CUDA(cudaEventElapsedTime(out_ms + i, p[0], p[1]));
+    }
+    *n_out = n;
     return CRS_OK;
 }
 
@@ -442,7 +458,7 @@ int crs_index_search(crs_index* ix, const void* queries, int nq, int k, float mi
                 float tau_pre = -INFINITY;
                 if (ix->metric == CRS_COSINE && min_similarity > -INFINITY)
                     tau_pre = min_similarity - eps_rel * 1.00390625f * ix->row_norm_bound;
-                if (ix->profiling) CRS_CUDA(cudaEventRecord(ix->ev0, st));
+                if (ix->profiling) CRS_CUDA(cudaEventRecord(ix->evs[ix->ev_count % 32][0], st));
                 if (use_gemm) {
                     // tensor-core accumulation may truncate instead of round: allow one ulp per term
                     fa.eps_rel = (float)((double)ix->dim_padded * ldexp(1.0, -23) * 1.05 * ix->eps_scale);
@@ -463,7 +479,7 @@ int crs_index_search(crs_index* ix, const void* queries, int nq, int k, float mi
                         ++launches;
                     }
                 }
-                if (ix->profiling) { CRS_CUDA(cudaEventRecord(ix->ev1, st)); ix->ev_valid = true; }
+                if (ix->profiling) { CRS_CUDA(cudaEventRecord(ix->evs[ix->ev_count % 32][1], st)); ++ix->ev_count; }
                 fa.mode = 0; fa.only_flagged = 0;
                 CRS_CUDA(cudaMemsetAsync(ix->n_flagged, 0, sizeof(int32_t), st));
                 CRS_CUDA(crs::launch_finalize(st, fa));
@@ -493,7 +509,7 @@ int crs_index_search(crs_index* ix, const void* queries, int nq, int k, float mi
             }
         } else {
             const int32_t min_raw = min_raw_for(ix, min_similarity);
-            if (ix->profiling) CRS_CUDA(cudaEventRecord(ix->ev0, st));
+            if (ix->profiling) CRS_CUDA(cudaEventRecord(ix->evs[ix->ev_count % 32][0], st));
             for (int q = 0; q < nq; ++q) {
                 const uint8_t* qc = ix->qcodes.p + (size_t)q * ix->row_bytes;
                 uint64_t* cd = ix->cand.p + (size_t)q * n_lists * M;
@@ -503,7 +519,7 @@ int crs_index_search(crs_index* ix, const void* queries, int nq, int k, float mi
                     CRS_CUDA(crs::launch_scan_b1(st, ix->codes, ix->count, ix->dim_padded, ix->dim, qc, min_raw, cd, plan));
                 ++launches;
             }
-            if (ix->profiling) { CRS_CUDA(cudaEventRecord(ix->ev1, st)); ix->ev_valid = true; }
+            if (ix->profiling) { CRS_CUDA(cudaEventRecord(ix->evs[ix->ev_count % 32][1], st)); ++ix->ev_count; }
             fa.mode = 1; fa.only_flagged = 0;
             CRS_CUDA(crs::launch_finalize(st, fa));
             ++launches;

@@ -32,8 +32,8 @@ encode_kernel(const float* __restrict__ src, int64_t n, int dim, int dim_padded,
     double n2 = 0.0;
     for (int c0 = 0; c0 < dim; c0 += 32) {
         const int c = c0 + lane;
-#pragma unroll 8
-        for (int r = 0; r < 32; ++r)
+#pragma unroll
+        for (int r = 0; r < 32; ++r)         // 32 independent loads in flight per lane
             t[r][lane] = (r < rows_here && c < dim) ? src[(row0 + r) * dim + c] : 0.f;
         __syncwarp();
         const int cmax = min(32, dim - c0);
@@ -55,12 +55,17 @@ encode_kernel(const float* __restrict__ src, int64_t n, int dim, int dim_padded,
     // pass 2: normalise + convert, lane = column so stores are coalesced
     for (int c0 = 0; c0 < dim_padded; c0 += 32) {
         const int c = c0 + lane;
-#pragma unroll 4
-        for (int r = 0; r < rows_here; ++r) {
+        float v[32];
+#pragma unroll
+        for (int r = 0; r < 32; ++r)         // issue all loads of the tile before the fp64 divides
+            v[r] = (r < rows_here && c < dim) ? src[(row0 + r) * dim + c] : 0.f;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            if (r >= rows_here) break;       // warp-uniform
             const double dv = __shfl_sync(CRS_FULL_MASK, div, r);
             const bool zr = __shfl_sync(CRS_FULL_MASK, (int)zero_row, r) != 0;
             double y = 0.0;
-            if (c < dim && !zr) y = (double)src[(row0 + r) * dim + c] / dv;
+            if (c < dim && !zr) y = (double)v[r] / dv;
             const int64_t o = (row0 + r) * (int64_t)dim_padded + c;
             if constexpr (STORE == CRS_F16) {
                 reinterpret_cast<__half*>(dst)[o] = __double2half(y);

@@ -81,6 +81,13 @@ class ShardIndex:
         N.check(self._lib.crs_index_last_kernel_ms(self._h, C.byref(ms)))
         return ms.value
 
+    def kernel_ms_history(self) -> list:
+        """Dominant-kernel device times of up to the last 32 searches, oldest first."""
+        buf = (C.c_float * 32)()
+        n = C.c_int()
+        N.check(self._lib.crs_index_kernel_ms_history(self._h, buf, 32, C.byref(n)))
+        return [buf[i] for i in range(n.value)]
+
     # ------------------------------------------------------------------ ingest
     def add(self, rows) -> None:
         """rows: float32 [n, dim] numpy array (host) or torch CUDA tensor (device)."""

@@ -98,6 +98,9 @@ int crs_index_set_option(crs_index* idx, const char* name, int64_t value);
 /* device time of the dominant kernel(s) (scan passes or GEMM) of the last search, from the
  * CUDA events recorded when "profiling" is on; waits for that search to finish. */
 int crs_index_last_kernel_ms(crs_index* idx, float* out_ms);
+/* the same for up to the last 32 searches (oldest first), so a benchmark can read the
+ * per-step kernel times after its timed loop without synchronising inside it. */
+int crs_index_kernel_ms_history(crs_index* idx, float* out_ms, int max_n, int* n_out);
 
 /* raw -> float similarity scale of this index: sim = raw * scale (1 for F16/BF16,
  * (a/127)^2 for I8, 1/dim for B1). */
