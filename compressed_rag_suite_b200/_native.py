@@ -35,6 +35,7 @@ SYMBOLS = {
     "crs_index_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64),
                                  C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "crs_index_search": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, _P, _P, _P]),
+    "crs_index_search_filtered": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, _P, _P, _P, _P]),
     "crs_index_last_stats": (C.c_int, [_P, _P]),
     "crs_index_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "crs_index_last_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),

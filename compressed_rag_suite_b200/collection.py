@@ -176,10 +176,18 @@ class Collection:
                 for key in ("ids", "documents", "metadatas", "distances"):
                     out[key].append([])
             return out
+        allow = None
         if where or where_document:
-            raise NotImplementedError("metadata / document filters are not wired to the GPU scan yet")
+            # predicates are dict / string work: evaluated here, pushed into the scans as a row bitmap
+            allow = np.fromiter((_where_ok(self._metas[r] or {}, where) and _doc_ok(self._docs[r] or "", where_document)
+                                 for r in range(n)), dtype=bool, count=n)
+            if not allow.any():
+                for _ in range(q.shape[0]):
+                    for key in ("ids", "documents", "metadatas", "distances"):
+                        out[key].append([])
+                return out
         k = min(int(n_results), n)
-        ids, raw, counts = self._index.search(q, k, min_similarity)
+        ids, raw, counts = self._index.search(q, k, min_similarity, allow=allow)
         sims = self._index.similarity(raw)
         for i in range(q.shape[0]):
             c = int(counts[i])

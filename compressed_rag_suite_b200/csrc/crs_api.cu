@@ -105,6 +105,7 @@ struct crs_index {
     DevScratch<int32_t> flags, counts_dev;
     DevScratch<uint32_t> ids_dev;
     DevScratch<uint8_t> scores_dev;
+    DevScratch<uint32_t> allow_dev;
     int32_t* n_flagged = nullptr;      // device counters: [0] this search, [1] since create
     crs_search_stats stats{};
     int profiling = 0;
@@ -228,7 +229,7 @@ int crs_index_destroy(crs_index* ix) {
         for (auto& p : ix->evs) { if (p[0]) cudaEventDestroy(p[0]); if (p[1]) cudaEventDestroy(p[1]); }
         ix->qsrc.release(); ix->qnorms.release(); ix->norms_tmp.release(); ix->qcodes.release();
         ix->stage_rows.release(); ix->cand.release(); ix->flags.release(); ix->counts_dev.release();
-        ix->ids_dev.release(); ix->scores_dev.release();
+        ix->ids_dev.release(); ix->scores_dev.release(); ix->allow_dev.release();
     }
     delete ix;
     return CRS_OK;
@@ -365,8 +366,8 @@ int crs_index_kernel_ms_history(crs_index* ix, float* out_ms, int max_n, int* n_
     return CRS_OK;
 }
 
-int crs_index_search(crs_index* ix, const void* queries, int nq, int k, float min_similarity,
-                     uint32_t* out_ids, void* out_scores, int32_t* out_counts) {
+static int search_impl(crs_index* ix, const void* queries, int nq, int k, float min_similarity,
+                       const uint32_t* allow_bits, uint32_t* out_ids, void* out_scores, int32_t* out_counts) {
     if (!ix) return fail(CRS_EINVAL, "index is NULL");
     if (nq < 0 || k <= 0) return fail(CRS_EINVAL, "nq must be >= 0 and k > 0");
     if (nq == 0) return CRS_OK;
@@ -378,7 +379,7 @@ int crs_index_search(crs_index* ix, const void* queries, int nq, int k, float mi
     if (is_float) { if (k <= 16) lpl = 1; else if (k <= 112) lpl = 4; else return fail(CRS_EINVAL, "k > 112 not supported for float stores"); }
     else { if (k <= 32) lpl = 1; else if (k <= 128) lpl = 4; else return fail(CRS_EINVAL, "k > 128 not supported"); }
     // batches go to the tcgen05 contraction (K4); single queries / unsupported shapes stream-scan (K1)
-    const bool use_gemm = is_float && ix->force_path != 0 && crs::gemm_supported(ix->dim_padded, k) &&
+    const bool use_gemm = is_float && allow_bits == nullptr && ix->force_path != 0 && crs::gemm_supported(ix->dim_padded, k) &&
                           (ix->force_path == 1 || nq >= 8);
     if (use_gemm) lpl = 1;
     const int M = 32 * lpl;
@@ -433,6 +434,16 @@ int crs_index_search(crs_index* ix, const void* queries, int nq, int k, float mi
         crs::ScanPlan plan;
         plan.lpl = lpl;
         plan.grid = ix->num_sms;
+        if (allow_bits) {                       // row bitmap of a where / where_document filter
+            const size_t words = (size_t)((ix->count + 31) / 32);
+            if (is_device_ptr(allow_bits)) {
+                plan.allow = allow_bits;
+            } else {
+                CRS_CUDA(ix->allow_dev.ensure(words));
+                CRS_CUDA(cudaMemcpyAsync(ix->allow_dev.p, allow_bits, words * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+                plan.allow = ix->allow_dev.p;
+            }
+        }
         const int n_lists = plan.grid;
         CRS_CUDA(ix->cand.ensure((size_t)nq * n_lists * M));
         CRS_CUDA(ix->flags.ensure((size_t)nq));
@@ -533,6 +544,17 @@ int crs_index_search(crs_index* ix, const void* queries, int nq, int k, float mi
     ix->stats.kernel_launches = launches;
     ix->stats.searches_total += nq;
     return CRS_OK;
+}
+
+int crs_index_search(crs_index* ix, const void* queries, int nq, int k, float min_similarity,
+                     uint32_t* out_ids, void* out_scores, int32_t* out_counts) {
+    return search_impl(ix, queries, nq, k, min_similarity, nullptr, out_ids, out_scores, out_counts);
+}
+
+int crs_index_search_filtered(crs_index* ix, const void* queries, int nq, int k, float min_similarity,
+                              const uint32_t* allow_bits, uint32_t* out_ids, void* out_scores,
+                              int32_t* out_counts) {
+    return search_impl(ix, queries, nq, k, min_similarity, allow_bits, out_ids, out_scores, out_counts);
 }
 
 int crs_index_fetch_rows(crs_index* ix, const uint32_t* ids, int n, void* out_codes) {

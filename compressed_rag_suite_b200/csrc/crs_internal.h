@@ -12,6 +12,7 @@ constexpr int kMaxListLen = 128;
 struct ScanPlan {
     int grid;          // persistent CTAs
     int lpl;           // list entries per lane (1 -> M = 32, 4 -> M = 128)
+    const uint32_t* allow = nullptr;   // optional row bitmap (bit r%32 of word r/32): metadata / document filter
 };
 
 // K0: fp32 rows -> stored codes (normalise for cosine, cast / quantise / sign-pack).

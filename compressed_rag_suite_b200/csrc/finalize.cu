@@ -191,7 +191,8 @@ constexpr int kExactWarps = 8;
 template <int LPL, bool BF16>
 __global__ void __launch_bounds__(kExactWarps * 32)
 exact_scan_kernel(const uint4* __restrict__ codes, int64_t n_rows, int chunks, const uint4* __restrict__ qcodes,
-                  int nq, const int32_t* __restrict__ flags, float min_similarity, uint64_t* __restrict__ cand) {
+                  int nq, const int32_t* __restrict__ flags, float min_similarity, uint64_t* __restrict__ cand,
+                  const uint32_t* __restrict__ allow) {
     constexpr int M = 32 * LPL;
     __shared__ uint64_t stage[kExactWarps * M];
     __shared__ int s_list[1024];
@@ -214,7 +215,7 @@ exact_scan_kernel(const uint4* __restrict__ codes, int64_t n_rows, int chunks, c
         for (int64_t r0 = (int64_t)blockIdx.x * blockDim.x + warp * 32; r0 < n_rows; r0 += stride) {
             const int64_t row = r0 + lane;
             uint64_t key = 0ull;
-            if (row < n_rows) {
+            if (row < n_rows && (allow == nullptr || ((allow[row >> 5] >> (row & 31)) & 1u))) {
                 const float s = exact_dot<BF16>(codes + row * chunks, qv, chunks);
                 if (s >= min_similarity) key = make_key(orderable_f32(s), (uint32_t)row);
             }
@@ -248,11 +249,11 @@ cudaError_t launch_exact_scan(cudaStream_t st, const void* codes, int64_t n, int
     const uint4* qv = reinterpret_cast<const uint4*>(qcodes);
     const int threads = kExactWarps * 32;
     if (plan.lpl == 1) {
-        if (bf16) exact_scan_kernel<1, true><<<plan.grid, threads, 0, st>>>(c, n, chunks, qv, nq, flags, min_similarity, cand);
-        else      exact_scan_kernel<1, false><<<plan.grid, threads, 0, st>>>(c, n, chunks, qv, nq, flags, min_similarity, cand);
+        if (bf16) exact_scan_kernel<1, true><<<plan.grid, threads, 0, st>>>(c, n, chunks, qv, nq, flags, min_similarity, cand, plan.allow);
+        else      exact_scan_kernel<1, false><<<plan.grid, threads, 0, st>>>(c, n, chunks, qv, nq, flags, min_similarity, cand, plan.allow);
     } else {
-        if (bf16) exact_scan_kernel<4, true><<<plan.grid, threads, 0, st>>>(c, n, chunks, qv, nq, flags, min_similarity, cand);
-        else      exact_scan_kernel<4, false><<<plan.grid, threads, 0, st>>>(c, n, chunks, qv, nq, flags, min_similarity, cand);
+        if (bf16) exact_scan_kernel<4, true><<<plan.grid, threads, 0, st>>>(c, n, chunks, qv, nq, flags, min_similarity, cand, plan.allow);
+        else      exact_scan_kernel<4, false><<<plan.grid, threads, 0, st>>>(c, n, chunks, qv, nq, flags, min_similarity, cand, plan.allow);
     }
     return cudaGetLastError();
 }

@@ -49,7 +49,8 @@ __device__ __forceinline__ float2 cvt_pair(uint32_t v) {
 template <int KIND, int NCH, int NW, int ITERS, int LPL, bool QREG>
 __global__ void __launch_bounds__((NW + 1) * 32, 1)
 scan_kernel(const uint8_t* __restrict__ codes, int64_t n_rows, const uint8_t* __restrict__ qcodes,
-            uint32_t ord_min, int32_t b1_dim, uint64_t* __restrict__ cand, int stages) {
+            uint32_t ord_min, int32_t b1_dim, uint64_t* __restrict__ cand, int stages,
+            const uint32_t* __restrict__ allow) {
     constexpr bool kFloat = (KIND == kF16 || KIND == kBF16);
     constexpr int ROWB = NCH * 128;
     constexpr int ROWS_PER_WARP = 4 * ITERS;
@@ -61,11 +62,15 @@ scan_kernel(const uint8_t* __restrict__ codes, int64_t n_rows, const uint8_t* __
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t full_bar[kScanMaxStages];
     __shared__ uint64_t empty_bar[kScanMaxStages];
+    // largest "M-th best" any warp of this CTA has reached: a key below it cannot be in the CTA's
+    // top-M, so every warp filters against it (cuts the insert rate by ~NW)
+    __shared__ unsigned long long cta_floor;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t n_tiles = (n_rows + TILE_ROWS - 1) / TILE_ROWS;
 
     if (threadIdx.x == 0) {
+        cta_floor = 0ull;
         for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NW); }
         fence_mbar_init();
     }
@@ -109,10 +114,12 @@ scan_kernel(const uint8_t* __restrict__ codes, int64_t n_rows, const uint8_t* __
     }
 
     WarpTopM<LPL> top; top.init();
+    uint64_t published = 0ull;
 
     int stage = 0; uint32_t phase = 0;
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         mbar_wait(&full_bar[stage], phase);
+        uint64_t floor_eff = u64max(top.floor_key, *reinterpret_cast<volatile unsigned long long*>(&cta_floor));
         const uint8_t* tile = smem + (size_t)stage * TILE_BYTES;
         uint32_t ord[ITERS];
 #pragma unroll
@@ -179,14 +186,22 @@ scan_kernel(const uint8_t* __restrict__ codes, int64_t n_rows, const uint8_t* __
         for (int it = 0; it < ITERS; ++it) {
             const int64_t row = t * TILE_ROWS + warp * ROWS_PER_WARP + it * 4 + grp;
             const uint64_t key = make_key(ord[it], (uint32_t)row);
-            const bool pass = (sub == 0) && (row < n_rows) && (ord[it] >= ord_min) && (key > top.floor_key);
+            bool pass = (sub == 0) && (row < n_rows) && (ord[it] >= ord_min) && (key > floor_eff);
+            if (allow != nullptr && pass) pass = (allow[row >> 5] >> (row & 31)) & 1u;   // where / where_document filter
             unsigned bal = __ballot_sync(CRS_FULL_MASK, pass);
             while (bal) {
                 const int src = __ffs(bal) - 1;
                 bal &= bal - 1;
                 const uint64_t kb = shfl_u64(key, src);
-                if (kb > top.floor_key) top.insert(kb, lane);
+                if (kb > floor_eff) {
+                    top.insert(kb, lane);
+                    floor_eff = u64max(floor_eff, top.floor_key);
+                }
             }
+        }
+        if (top.floor_key > published) {                 // warp-uniform; non-zero only once the list is full
+            published = top.floor_key;
+            if (lane == 0) atomicMax(&cta_floor, (unsigned long long)published);
         }
     }
 
@@ -204,9 +219,159 @@ scan_kernel(const uint8_t* __restrict__ codes, int64_t n_rows, const uint8_t* __
     }
 }
 
+// K2 / K3 for short rows (128 or 256 bytes, e.g. 1024-bit codes): one THREAD per row.
+// With 8 lanes per row a 128-byte row costs three shuffles, a key build and a ballot per 16
+// bytes of payload and the kernel is issue-bound (ncu: 19.6 warp-instructions per row, 3.9 TB/s).
+// Here lane l walks row l of its warp's 32 rows in the rotated chunk order (c + l) mod CH, so
+// a quarter-warp still touches 8 distinct 16-byte bank groups (conflict-free LDS.128) and each
+// lane keeps the query pre-rotated the same way in registers.  Integer scores are
+// order-independent, so the result is unchanged.  Same ring, same top-M, same output.
+template <int KIND, int NCH, int NW, int LPL>
+__global__ void __launch_bounds__((NW + 1) * 32, 1)
+scan_rows_kernel(const uint8_t* __restrict__ codes, int64_t n_rows, const uint8_t* __restrict__ qcodes,
+                 uint32_t ord_min, int32_t b1_dim, uint64_t* __restrict__ cand, int stages,
+                 const uint32_t* __restrict__ allow) {
+    static_assert(KIND == kI8 || KIND == kB1, "integer stores only");
+    static_assert(NCH == 1 || NCH == 2, "rows of 128 or 256 bytes");
+    constexpr int ROWB = NCH * 128;
+    constexpr int CH = NCH * 8;                       // 16-byte chunks per row
+    constexpr int TILE_ROWS = NW * 32;
+    constexpr int TILE_BYTES = TILE_ROWS * ROWB;
+    constexpr int M = 32 * LPL;
+
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t full_bar[kScanMaxStages];
+    __shared__ uint64_t empty_bar[kScanMaxStages];
+    __shared__ unsigned long long cta_floor;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n_tiles = (n_rows + TILE_ROWS - 1) / TILE_ROWS;
+
+    if (threadIdx.x == 0) {
+        cta_floor = 0ull;
+        for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NW); }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == NW) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                const int64_t r0 = t * TILE_ROWS;
+                const uint32_t bytes = (uint32_t)(min((int64_t)TILE_ROWS, n_rows - r0) * ROWB);
+                mbar_arrive_expect_tx(&full_bar[stage], bytes);
+                bulk_g2s(smem + (size_t)stage * TILE_BYTES, codes + r0 * ROWB, bytes, &full_bar[stage]);
+                if (++stage == stages) { stage = 0; phase ^= 1; }
+            }
+        }
+        return;
+    }
+
+    uint32_t qi[CH * 4];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        const uint4 v = *reinterpret_cast<const uint4*>(qcodes + ((c + lane) & (CH - 1)) * 16);
+        qi[c * 4 + 0] = v.x; qi[c * 4 + 1] = v.y; qi[c * 4 + 2] = v.z; qi[c * 4 + 3] = v.w;
+    }
+
+    WarpTopM<LPL> top; top.init();
+    uint64_t published = 0ull;
+    int stage = 0; uint32_t phase = 0;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        mbar_wait(&full_bar[stage], phase);
+        uint64_t floor_eff = u64max(top.floor_key, *reinterpret_cast<volatile unsigned long long*>(&cta_floor));
+        const int row_in_tile = warp * 32 + lane;
+        const int64_t row = t * TILE_ROWS + row_in_tile;
+        const uint8_t* rp = smem + (size_t)stage * TILE_BYTES + (size_t)row_in_tile * ROWB;
+        int acc = 0;
+        if (row < n_rows) {
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                const uint4 v = *reinterpret_cast<const uint4*>(rp + ((c + lane) & (CH - 1)) * 16);
+                if constexpr (KIND == kI8) {
+                    acc = __dp4a((int)v.x, (int)qi[c * 4 + 0], acc);
+                    acc = __dp4a((int)v.y, (int)qi[c * 4 + 1], acc);
+                    acc = __dp4a((int)v.z, (int)qi[c * 4 + 2], acc);
+                    acc = __dp4a((int)v.w, (int)qi[c * 4 + 3], acc);
+                } else {
+                    acc += __popc(v.x ^ qi[c * 4 + 0]) + __popc(v.y ^ qi[c * 4 + 1]) +
+                           __popc(v.z ^ qi[c * 4 + 2]) + __popc(v.w ^ qi[c * 4 + 3]);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+
+        if constexpr (KIND == kB1) acc = b1_dim - 2 * acc;
+        const uint32_t ord = orderable_i32(acc);
+        // cheap 32-bit pre-test on the score; the 64-bit key is only built for survivors
+        bool pass = (row < n_rows) && (ord >= ord_min) && (ord >= key_ord(floor_eff));
+        uint64_t key = 0ull;
+        if (pass) {
+            key = make_key(ord, (uint32_t)row);
+            pass = key > floor_eff;
+            if (allow != nullptr && pass) pass = (allow[row >> 5] >> (row & 31)) & 1u;
+        }
+        unsigned bal = __ballot_sync(CRS_FULL_MASK, pass);
+        while (bal) {
+            const int src = __ffs(bal) - 1;
+            bal &= bal - 1;
+            const uint64_t kb = shfl_u64(key, src);
+            if (kb > floor_eff) {
+                top.insert(kb, lane);
+                floor_eff = u64max(floor_eff, top.floor_key);
+            }
+        }
+        if (top.floor_key > published) {
+            published = top.floor_key;
+            if (lane == 0) atomicMax(&cta_floor, (unsigned long long)published);
+        }
+    }
+
+    warp_sort_desc<LPL>(top.e, lane);
+    named_barrier_1<NW * 32>();
+    uint64_t* stage_keys = reinterpret_cast<uint64_t*>(smem);
+    block_merge_lists<LPL, NW>(top.e, stage_keys, warp, lane);
+    if (warp == 0) {
+#pragma unroll
+        for (int sl = 0; sl < LPL; ++sl)
+            cand[(size_t)blockIdx.x * M + lane * LPL + sl] = top.e[sl];
+    }
+}
+
+template <int KIND, int NCH, int NW, int LPL>
+static cudaError_t launch_rows(cudaStream_t st, const void* codes, int64_t n, const void* qcodes, uint32_t ord_min,
+                               int32_t b1_dim, uint64_t* cand, int grid, const uint32_t* allow) {
+    constexpr int TILE_BYTES = NW * 32 * NCH * 128;
+    constexpr int M = 32 * LPL;
+    int stages = (200 * 1024) / TILE_BYTES;
+    if (stages > kScanMaxStages) stages = kScanMaxStages;
+    size_t smem = (size_t)stages * TILE_BYTES;
+    const size_t merge_bytes = (size_t)NW * M * sizeof(uint64_t);
+    if (smem < merge_bytes) smem = merge_bytes;
+    auto kern = scan_rows_kernel<KIND, NCH, NW, LPL>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, (NW + 1) * 32, smem, st>>>(reinterpret_cast<const uint8_t*>(codes), n,
+                                            reinterpret_cast<const uint8_t*>(qcodes), ord_min, b1_dim, cand, stages, allow);
+    return cudaGetLastError();
+}
+
+template <int KIND, int NCH>
+static cudaError_t rows_by_lpl(cudaStream_t st, const void* codes, int64_t n, const void* qcodes, uint32_t ord_min,
+                               int32_t b1_dim, uint64_t* cand, const ScanPlan& p) {
+    constexpr int NW = (NCH == 1) ? 16 : 8;          // 64 query registers per lane at NCH = 2
+    if (p.lpl == 1) return launch_rows<KIND, NCH, NW, 1>(st, codes, n, qcodes, ord_min, b1_dim, cand, p.grid, p.allow);
+    if (p.lpl == 4) return launch_rows<KIND, NCH, NW, 4>(st, codes, n, qcodes, ord_min, b1_dim, cand, p.grid, p.allow);
+    return cudaErrorInvalidValue;
+}
+
 template <int KIND, int NCH, int NW, int ITERS, int LPL, bool QREG>
 static cudaError_t launch_one(cudaStream_t st, const void* codes, int64_t n, const void* qcodes, uint32_t ord_min,
-                              int32_t b1_dim, uint64_t* cand, int grid) {
+                              int32_t b1_dim, uint64_t* cand, int grid, const uint32_t* allow) {
     constexpr int TILE_BYTES = NW * 4 * ITERS * NCH * 128;
     constexpr int M = 32 * LPL;
     int stages = (200 * 1024) / TILE_BYTES;
@@ -219,15 +384,15 @@ static cudaError_t launch_one(cudaStream_t st, const void* codes, int64_t n, con
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, (NW + 1) * 32, smem, st>>>(reinterpret_cast<const uint8_t*>(codes), n,
-                                            reinterpret_cast<const uint8_t*>(qcodes), ord_min, b1_dim, cand, stages);
+                                            reinterpret_cast<const uint8_t*>(qcodes), ord_min, b1_dim, cand, stages, allow);
     return cudaGetLastError();
 }
 
 template <int KIND, int NCH, int NW, int ITERS, bool QREG>
 static cudaError_t by_lpl(cudaStream_t st, const void* codes, int64_t n, const void* qcodes, uint32_t ord_min,
                           int32_t b1_dim, uint64_t* cand, const ScanPlan& p) {
-    if (p.lpl == 1) return launch_one<KIND, NCH, NW, ITERS, 1, QREG>(st, codes, n, qcodes, ord_min, b1_dim, cand, p.grid);
-    if (p.lpl == 4) return launch_one<KIND, NCH, NW, ITERS, 4, QREG>(st, codes, n, qcodes, ord_min, b1_dim, cand, p.grid);
+    if (p.lpl == 1) return launch_one<KIND, NCH, NW, ITERS, 1, QREG>(st, codes, n, qcodes, ord_min, b1_dim, cand, p.grid, p.allow);
+    if (p.lpl == 4) return launch_one<KIND, NCH, NW, ITERS, 4, QREG>(st, codes, n, qcodes, ord_min, b1_dim, cand, p.grid, p.allow);
     return cudaErrorInvalidValue;
 }
 
@@ -258,8 +423,8 @@ template <int KIND>
 static cudaError_t by_rowbytes_int(cudaStream_t st, const void* codes, int64_t n, int nch, const void* qcodes,
                                    uint32_t ord_min, int32_t b1_dim, uint64_t* cand, const ScanPlan& p) {
     switch (nch) {   // row_bytes = 128 * nch
-        case 1:  return by_lpl<KIND, 1, 16, 8, true>(st, codes, n, qcodes, ord_min, b1_dim, cand, p);
-        case 2:  return by_lpl<KIND, 2, 16, 4, true>(st, codes, n, qcodes, ord_min, b1_dim, cand, p);
+        case 1:  return rows_by_lpl<KIND, 1>(st, codes, n, qcodes, ord_min, b1_dim, cand, p);
+        case 2:  return rows_by_lpl<KIND, 2>(st, codes, n, qcodes, ord_min, b1_dim, cand, p);
         case 3:  return by_lpl<KIND, 3, 16, 2, true>(st, codes, n, qcodes, ord_min, b1_dim, cand, p);
         case 4:  return by_lpl<KIND, 4, 16, 2, true>(st, codes, n, qcodes, ord_min, b1_dim, cand, p);
         case 6:  return by_lpl<KIND, 6, 16, 1, true>(st, codes, n, qcodes, ord_min, b1_dim, cand, p);

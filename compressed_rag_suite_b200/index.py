@@ -105,7 +105,7 @@ class ShardIndex:
         N.check(self._lib.crs_index_add(self._h, a.ctypes.data_as(C.c_void_p), a.shape[0], N.CRS_F32))
 
     # ------------------------------------------------------------------ search
-    def search(self, queries, k: int, min_similarity: float = -math.inf):
+    def search(self, queries, k: int, min_similarity: float = -math.inf, allow=None):
         """-> (ids uint32 [nq,k], raw scores f32|i32 [nq,k], counts i32 [nq]).
 
         numpy in -> numpy out (synchronous); torch CUDA in -> torch CUDA out (enqueued on
@@ -138,10 +138,28 @@ class ShardIndex:
         ids = np.empty((nq, k), dtype=np.uint32)
         sc = np.empty((nq, k), dtype=np.int32 if self.is_int else np.float32)
         cnt = np.empty((nq,), dtype=np.int32)
-        N.check(self._lib.crs_index_search(self._h, q.ctypes.data_as(C.c_void_p), nq, int(k), float(min_similarity),
-                                           ids.ctypes.data_as(C.c_void_p), sc.ctypes.data_as(C.c_void_p),
-                                           cnt.ctypes.data_as(C.c_void_p)))
+        if allow is None:
+            N.check(self._lib.crs_index_search(self._h, q.ctypes.data_as(C.c_void_p), nq, int(k), float(min_similarity),
+                                               ids.ctypes.data_as(C.c_void_p), sc.ctypes.data_as(C.c_void_p),
+                                               cnt.ctypes.data_as(C.c_void_p)))
+        else:
+            bits = self.pack_allow(allow)
+            N.check(self._lib.crs_index_search_filtered(self._h, q.ctypes.data_as(C.c_void_p), nq, int(k),
+                                                        float(min_similarity), bits.ctypes.data_as(C.c_void_p),
+                                                        ids.ctypes.data_as(C.c_void_p), sc.ctypes.data_as(C.c_void_p),
+                                                        cnt.ctypes.data_as(C.c_void_p)))
         return ids, sc, cnt
+
+    def pack_allow(self, allow) -> np.ndarray:
+        """bool mask over the local rows -> uint32 bitmap (bit r%32 of word r/32)."""
+        a = np.asarray(allow, dtype=bool).reshape(-1)
+        n = len(self)
+        if a.shape[0] != n:
+            raise ValueError(f"allow mask has {a.shape[0]} entries, index has {n} rows")
+        pad = (-n) % 32
+        if pad:
+            a = np.concatenate([a, np.zeros(pad, dtype=bool)])
+        return np.packbits(a.reshape(-1, 32), axis=1, bitorder="little").view(np.uint32).reshape(-1).copy()
 
     def similarity(self, raw):
         """raw scores -> float32 cosine-domain similarity (numpy)."""

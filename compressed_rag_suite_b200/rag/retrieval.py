@@ -121,7 +121,8 @@ class ContextRetriever:
             logger.error(f"Retrieval failed: {e}")
             raise
 
-    def retrieve_batch(self, queries: List[str], top_k: Optional[int] = None) -> List[List[Dict]]:
+    def retrieve_batch(self, queries: List[str], top_k: Optional[int] = None,
+                       filters: Optional[dict] = None) -> List[List[Dict]]:
         """Many queries at once: one embedder call, one batched GPU search, one MMR launch."""
         k = top_k or self.top_k
         if not queries:
@@ -137,7 +138,8 @@ class ContextRetriever:
             bound = self._pushdown_similarity()
             if bound is not None:
                 extra["min_similarity"] = bound
-            results = col.query(query_embeddings=emb, n_results=min(self._n_fetch(k), col.count()), **extra)
+            results = col.query(query_embeddings=emb, n_results=min(self._n_fetch(k), col.count()),
+                                where=filters, **extra)
             lists = [self._post(q, self._format(results, i), k) for i, q in enumerate(queries)]
             if self.diversity_penalty > 0:
                 lists = self._apply_diversity_batch(lists)

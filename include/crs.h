@@ -90,6 +90,14 @@ int crs_index_info(const crs_index* idx, int32_t* dim, int32_t* dim_padded, int6
  *   out_counts : [nq] number of valid entries per query */
 int crs_index_search(crs_index* idx, const void* queries, int nq, int k, float min_similarity,
                      uint32_t* out_ids, void* out_scores, int32_t* out_counts);
+/* the same with the `where` / `where_document` arguments of collection.query
+ * (rag/indexing.py:129-130,174-175; rag/retrieval.py:97,120): the host evaluates the
+ * metadata / document predicates (they are string and dict work) and passes the result as a
+ * row bitmap — bit (r % 32) of word (r / 32) set = local row r may be returned;
+ * ceil(count / 32) words, host or device.  NULL = no filter. */
+int crs_index_search_filtered(crs_index* idx, const void* queries, int nq, int k, float min_similarity,
+                              const uint32_t* allow_bits, uint32_t* out_ids, void* out_scores,
+                              int32_t* out_counts);
 int crs_index_last_stats(const crs_index* idx, crs_search_stats* out);
 /* Tuning / test hooks: name in {"force_path" (-1 auto, 0 scan, 1 gemm), "force_exact"
  * (1 = always run the fp64 pass), "eps_scale" (x1000), "profiling" (1 = bracket the

@@ -304,3 +304,30 @@ def test_gemm_path_duplicates_and_fallback():
     assert ix.last_stats()["path"] == 1
     assert list(ids[0]) == [7] + list(range(2000, 2009))
     assert ix.last_stats()["uncertified_total"] >= 1
+
+
+# ---------------------------------------------------------------- N3: row-bitmap filters
+@pytest.mark.parametrize("store", ["f16", "bf16", "i8", "b1"])
+def test_filtered_search_equals_oracle_on_allowed_rows(store):
+    n = 20000
+    x, centres = clustered(n, 384, seed=140)
+    q = queries_for(centres, x, 12, seed=141)           # 12 queries: would take the GEMM path unfiltered
+    ix = ShardIndex(384, dtype=store)
+    ix.add(x)
+    rng = np.random.default_rng(142)
+    codes = encode.encode_rows(x, store)
+    qc = search.encode_queries(q, store)
+    for frac in (0.5, 0.01, 0.0003):
+        allow = rng.random(n) < frac
+        allow[17] = True
+        rows = np.nonzero(allow)[0]
+        want = search.search(codes[rows], qc, store, 384, 10)
+        got = ix.search(q, 10, allow=allow)
+        assert np.array_equal(got[2], want[2])
+        for i in range(len(q)):
+            c = want[2][i]
+            assert np.array_equal(got[0][i, :c], rows[want[0][i, :c].astype(np.int64)].astype(np.uint32))
+            assert np.array_equal(got[1][i, :c], want[1][i, :c])
+            assert np.all(got[0][i, c:] == 0xFFFFFFFF)
+    with pytest.raises(ValueError):
+        ix.search(q, 10, allow=np.ones(5, bool))

@@ -155,3 +155,35 @@ def test_persist_directory_roundtrip(tmp_path):
     assert b.search(x[7], top_k=5) == want
     b.create_index(chunks[:10], x[:10])                 # ids collide across processes: ignored
     assert b.get_stats()["count"] == 50
+
+
+def test_where_filters_equal_oracle_chroma():
+    rng = np.random.default_rng(2718)
+    n, dim = 400, 384
+    x = rng.standard_normal((n, dim)).astype(np.float32)
+    texts = [f"{'alpha' if i % 3 else 'omega'} body text {i}" for i in range(n)]
+    chunks = [Chunk(t, f"chunk_{i}", 0, len(t), page_number=i % 11, section=f"s{i % 4}" if i % 5 else None)
+              for i, t in enumerate(texts)]
+    vs = VectorStore({"collection_name": "filters"})
+    vs.create_index(chunks, x)
+    fake_chroma.PRECISION = "f16"
+    oc = fake_chroma.Client().create_collection("filters", {"hnsw:space": "cosine"})
+    metas = [VectorStore._chunk_metadata(c, ("page_number", "section", "tokens")) for c in chunks]
+    oc.add(ids=[c.chunk_id for c in chunks], embeddings=x, documents=texts, metadatas=metas)
+    q = rng.standard_normal(dim).astype(np.float32)
+    cases = [({"page_number": 3}, None), ({"page_number": {"$gte": 9}}, None),
+             ({"$and": [{"page_number": {"$lt": 4}}, {"section": {"$ne": "s1"}}]}, None),
+             ({"$or": [{"section": "s2"}, {"page_number": {"$in": [0, 10]}}]}, None),
+             (None, {"$contains": "omega"}), ({"page_number": {"$nin": [1, 2, 3]}}, {"$not_contains": "omega"}),
+             ({"page_number": 99}, None)]
+    for where, where_doc in cases:
+        got = vs.search(q, top_k=7, where=where, where_document=where_doc)
+        want = oc.query(q[None, :], 7, where, where_doc)
+        for key in ("ids", "documents", "metadatas", "distances"):
+            assert got[key] == want[key], (where, where_doc, key)
+    emb = TableEmbedder()
+    emb.table["find alpha"] = q
+    r = ContextRetriever(vs, emb, {"top_k": 3, "rerank": True, "diversity_penalty": 0.2})
+    out = r.retrieve("find alpha", filters={"page_number": 5})
+    assert len(out) == 3 and all(c["metadata"]["page_number"] == 5 for c in out)
+    assert r.retrieve_batch(["find alpha"], filters={"page_number": 5}) == [out]
