@@ -379,8 +379,8 @@ static int search_impl(crs_index* ix, const void* queries, int nq, int k, float 
     if (is_float) { if (k <= 16) lpl = 1; else if (k <= 112) lpl = 4; else return fail(CRS_EINVAL, "k > 112 not supported for float stores"); }
     else { if (k <= 32) lpl = 1; else if (k <= 128) lpl = 4; else return fail(CRS_EINVAL, "k > 128 not supported"); }
     // batches go to the tcgen05 contraction (K4); single queries / unsupported shapes stream-scan (K1)
-    const bool use_gemm = is_float && allow_bits == nullptr && ix->force_path != 0 && crs::gemm_supported(ix->dim_padded, k) &&
-                          (ix->force_path == 1 || nq >= 8);
+    const bool use_gemm = (is_float || ix->store == CRS_I8) && allow_bits == nullptr && ix->force_path != 0 &&
+                          crs::gemm_supported((int)ix->row_bytes, k) && (ix->force_path == 1 || nq >= 8);
     if (use_gemm) lpl = 1;
     const int M = 32 * lpl;
 
@@ -476,8 +476,10 @@ static int search_impl(crs_index* ix, const void* queries, int nq, int k, float 
                     if (tau_pre > -INFINITY)
                         tau_pre = min_similarity - fa.eps_rel * 1.00390625f * ix->row_norm_bound;
                     int n_slices = 0;
-                    CRS_CUDA(crs::launch_gemm_topk(st, ix->codes, ix->count, ix->dim_padded, fa.bf16, ix->qcodes.p, nq, k,
-                                                   tau_pre, ix->cand.p, ix->num_sms, ix->gemm_cluster, &n_slices));
+                    uint32_t tau_bits;
+                    memcpy(&tau_bits, &tau_pre, sizeof(tau_bits));
+                    CRS_CUDA(crs::launch_gemm_topk(st, ix->codes, ix->count, (int)ix->row_bytes, fa.bf16 ? 1 : 0, ix->qcodes.p,
+                                                   nq, k, tau_bits, ix->cand.p, ix->num_sms, ix->gemm_cluster, &n_slices));
                     ++launches;
                     fa.n_lists = n_slices;
                     fa.list_len = crs::gemm_list_len(k);
@@ -521,6 +523,16 @@ static int search_impl(crs_index* ix, const void* queries, int nq, int k, float 
         } else {
             const int32_t min_raw = min_raw_for(ix, min_similarity);
             if (ix->profiling) CRS_CUDA(cudaEventRecord(ix->evs[ix->ev_count % 32][0], st));
+            if (use_gemm) {
+                // K5: exact int32 scores straight from the tensor cores; each slice list keeps >= k keys
+                int n_slices = 0;
+                CRS_CUDA(crs::launch_gemm_topk(st, ix->codes, ix->count, (int)ix->row_bytes, 2, ix->qcodes.p, nq, k,
+                                               (uint32_t)min_raw, ix->cand.p, ix->num_sms, ix->gemm_cluster, &n_slices));
+                ++launches;
+                fa.n_lists = n_slices;
+                fa.list_len = crs::gemm_list_len(k);
+                ix->stats.path = 1; ix->stats.grid = n_slices * ((nq + 127) / 128); ix->stats.list_len = fa.list_len;
+            } else {
             for (int q = 0; q < nq; ++q) {
                 const uint8_t* qc = ix->qcodes.p + (size_t)q * ix->row_bytes;
                 uint64_t* cd = ix->cand.p + (size_t)q * n_lists * M;
@@ -529,6 +541,7 @@ static int search_impl(crs_index* ix, const void* queries, int nq, int k, float 
                 else
                     CRS_CUDA(crs::launch_scan_b1(st, ix->codes, ix->count, ix->dim_padded, ix->dim, qc, min_raw, cd, plan));
                 ++launches;
+            }
             }
             if (ix->profiling) { CRS_CUDA(cudaEventRecord(ix->evs[ix->ev_count % 32][1], st)); ++ix->ev_count; }
             fa.mode = 1; fa.only_flagged = 0;

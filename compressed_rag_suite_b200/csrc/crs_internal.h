@@ -64,13 +64,15 @@ cudaError_t launch_exact_scan(cudaStream_t st, const void* codes, int64_t n, int
                               const void* qcodes, int nq, const int32_t* flags, float min_similarity,
                               uint64_t* cand, const ScanPlan& plan);
 
-// K4: tcgen05 Q*C^T with fused top-L epilogue (fp16 / bf16 stores, Dp <= 384, k <= 24).
-// Writes one sorted list of gemm_list_len(k) keys per (query, corpus slice), list stride 32;
-// *n_slices_out = number of lists per query.
-bool gemm_supported(int dim_padded, int k);
+// K4 / K5: tcgen05 Q*C^T with fused top-L epilogue.  kind 0 = fp16, 1 = bf16 (kind::f16, f32
+// accumulate, candidates for finalize mode 0), 2 = int8 (kind::i8, exact int32 scores, finalize
+// mode 1).  Rows of 128..768 bytes, k <= 24.  Writes one sorted list of gemm_list_len(k) keys per
+// (query, corpus slice), list stride 32; *n_slices_out = number of lists per query.
+// tau_pre_bits: threshold as float bits (kind 0/1) or int32 bits (kind 2).
+bool gemm_supported(int row_bytes, int k);
 int gemm_list_len(int k);
-cudaError_t launch_gemm_topk(cudaStream_t st, const void* codes, int64_t n, int dim_padded, bool bf16,
-                             const void* qcodes, int nq, int k, float tau_pre, uint64_t* cand, int num_sms,
+cudaError_t launch_gemm_topk(cudaStream_t st, const void* codes, int64_t n, int row_bytes, int kind,
+                             const void* qcodes, int nq, int k, uint32_t tau_pre_bits, uint64_t* cand, int num_sms,
                              int cluster /*0 = auto, else 1|2|4 query tiles per multicast cluster*/, int* n_slices_out);
 
 // K7: merge G lists of k_in (id, raw score) per query into the global top k_out.

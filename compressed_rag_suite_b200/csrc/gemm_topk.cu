@@ -79,6 +79,14 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// kind::i8: signed 8-bit operands, int32 accumulators, K = 32 per instruction (K5)
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -122,46 +130,66 @@ __device__ __forceinline__ void list_insert(uint64_t (&a)[L], uint64_t x) {
 // tree max against the running threshold.  Slow path (rare once the list is warm): a hit mask
 // and ONE copy of the insert code, walked only over this thread's own hits, so a warp runs
 // max-over-lanes(hits) insert bodies instead of one per column any lane hit.
-template <int L>
-__device__ __forceinline__ void slab_scan(const uint32_t (&r)[32], int64_t row0, int64_t n_rows, float tau_pre,
-                                          float& tau, uint64_t (&best)[L]) {
-    float m[16];
+template <bool INT> struct ScoreT { using type = float; };
+template <> struct ScoreT<true> { using type = int32_t; };
+
+template <bool INT>
+__device__ __forceinline__ typename ScoreT<INT>::type score_of(uint32_t bits) {
+    if constexpr (INT) return (int32_t)bits; else return __uint_as_float(bits);
+}
+template <bool INT>
+__device__ __forceinline__ uint32_t ord_of(typename ScoreT<INT>::type v) {
+    if constexpr (INT) return orderable_i32(v); else return orderable_f32(v);
+}
+template <bool INT>
+__device__ __forceinline__ typename ScoreT<INT>::type from_ord(uint32_t o) {
+    if constexpr (INT) return unorderable_i32(o); else return unorderable_f32(o);
+}
+template <typename T> __device__ __forceinline__ T smax(T a, T b) { return a > b ? a : b; }
+template <> __device__ __forceinline__ float smax<float>(float a, float b) { return fmaxf(a, b); }
+
+template <int L, bool INT>
+__device__ __forceinline__ void slab_scan(const uint32_t (&r)[32], int64_t row0, int64_t n_rows,
+                                          typename ScoreT<INT>::type tau_pre, typename ScoreT<INT>::type& tau,
+                                          uint64_t (&best)[L]) {
+    using T = typename ScoreT<INT>::type;
+    T m[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) m[i] = fmaxf(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+    for (int i = 0; i < 16; ++i) m[i] = smax<T>(score_of<INT>(r[2 * i]), score_of<INT>(r[2 * i + 1]));
 #pragma unroll
     for (int w = 8; w >= 1; w >>= 1) {
 #pragma unroll
-        for (int i = 0; i < w; ++i) m[i] = fmaxf(m[i], m[i + w]);
+        for (int i = 0; i < w; ++i) m[i] = smax<T>(m[i], m[i + w]);
     }
     if (m[0] >= tau) {
         unsigned mask = 0;
-        float tmp[32];                       // dynamically indexed -> local memory, touched on this path only
+        T tmp[32];                           // dynamically indexed -> local memory, touched on this path only
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-            const float v = __uint_as_float(r[i]);
+            const T v = score_of<INT>(r[i]);
             tmp[i] = v;
             mask |= (v >= tau) ? (1u << i) : 0u;
         }
         while (mask) {
             const int i = __ffs(mask) - 1;
             mask &= mask - 1;
-            const float v = tmp[i];
+            const T v = tmp[i];
             const int64_t row = row0 + i;
             if (v >= tau && row < n_rows) {
-                const uint64_t key = make_key(orderable_f32(v), (uint32_t)row);
+                const uint64_t key = make_key(ord_of<INT>(v), (uint32_t)row);
                 if (key > best[L - 1]) {
                     list_insert<L>(best, key);
-                    if (best[L - 1] != 0ull) tau = fmaxf(tau_pre, unorderable_f32(key_ord(best[L - 1])));
+                    if (best[L - 1] != 0ull) tau = smax<T>(tau_pre, from_ord<INT>(key_ord(best[L - 1])));
                 }
             }
         }
     }
 }
 
-template <int KCH, int L, int CS>
+template <int KCH, int L, int CS, bool INT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
-                 int64_t n_rows, int n_qtiles, int n_slices, uint32_t idesc, float tau_pre,
+                 int64_t n_rows, int n_qtiles, int n_slices, uint32_t idesc, uint32_t tau_pre_bits,
                  uint64_t* __restrict__ cand, int nq, int list_stride) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[kStages], empty_bar[kStages], a_bar, tfull_bar[2], tempty_bar[2];
@@ -203,7 +231,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         if (lane == 0) {
             mbar_arrive_expect_tx(&a_bar, KCH * kAChunkBytes);
             for (int kc = 0; kc < KCH; ++kc)
-                tma_load_2d(smem_a + kc * kAChunkBytes, &map_q, kc * kChunkK, qtile * kTileQ, &a_bar);
+                tma_load_2d(smem_a + kc * kAChunkBytes, &map_q, kc * (INT ? 128 : kChunkK), qtile * kTileQ, &a_bar);
             int stage = 0; uint32_t phase = 0;
             for (int t = 0; t < n_tiles; ++t) {
                 const int row0 = (int)((tile_lo + t) * kTileC);
@@ -211,10 +239,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full_bar[stage], kBStageBytes);      // all CS pieces land here
                     if constexpr (CS == 1) {
-                        tma_load_2d(smem_b + stage * kBStageBytes, &map_c, kc * kChunkK, row0, &full_bar[stage]);
+                        tma_load_2d(smem_b + stage * kBStageBytes, &map_c, kc * (INT ? 128 : kChunkK), row0, &full_bar[stage]);
                     } else {
                         constexpr int kPieceRows = kTileC / CS;
-                        tma_load_2d_mc(smem_b + stage * kBStageBytes + crank * kPieceRows * 128, &map_c, kc * kChunkK,
+                        tma_load_2d_mc(smem_b + stage * kBStageBytes + crank * kPieceRows * 128, &map_c, kc * (INT ? 128 : kChunkK),
                                        row0 + crank * kPieceRows, &full_bar[stage], kMask);
                     }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -240,7 +268,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                     const uint64_t b_desc = make_smem_desc(smem_u32(smem_b + stage * kBStageBytes));
 #pragma unroll
                     for (int k = 0; k < kChunkK / 16; ++k)          // +32 bytes per K=16 step inside the swizzle row
-                        umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kc | k) != 0);
+                        if constexpr (INT) umma_i8(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kc | k) != 0);
+                        else umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kc | k) != 0);
                     if constexpr (CS == 1) umma_commit(&empty_bar[stage]);   // slot reusable once these MMAs retire
                     else umma_commit_mc(&empty_bar[stage], kMask);          // ... in every CTA that writes into it
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -258,7 +287,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         for (int i = 0; i < L; ++i) best[i] = 0ull;
         // running threshold: L-th best so far.  Padding rows of the last query tile (all-zero
         // queries, every score 0) must never enter the slow path: their threshold is +inf.
-        float tau = (q < nq) ? tau_pre : INFINITY;
+        using T = typename ScoreT<INT>::type;
+        const T tau_pre = score_of<INT>(tau_pre_bits);
+        T tau;
+        if constexpr (INT) tau = (q < nq) ? tau_pre : INT32_MAX; else tau = (q < nq) ? tau_pre : INFINITY;
         for (int t = 0; t < n_tiles; ++t) {
             const int buf = t & 1;
             const uint32_t tphase = (t >> 1) & 1;
@@ -273,11 +305,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 #pragma unroll 1
             for (int slab = 0; slab < kTileC / 32; slab += 2) {
                 tmem_ld32(taddr + (slab + 1) * 32, rb);
-                slab_scan<L>(ra, row0 + slab * 32, n_rows, tau_pre, tau, best);
+                slab_scan<L, INT>(ra, row0 + slab * 32, n_rows, tau_pre, tau, best);
                 __syncwarp();                                       // tcgen05.ld / wait are .aligned: reconverge first
                 tmem_ld_wait();
                 if (slab + 2 < kTileC / 32) tmem_ld32(taddr + (slab + 2) * 32, ra);
-                slab_scan<L>(rb, row0 + (slab + 1) * 32, n_rows, tau_pre, tau, best);
+                slab_scan<L, INT>(rb, row0 + (slab + 1) * 32, n_rows, tau_pre, tau, best);
                 __syncwarp();
                 tmem_ld_wait();
             }
@@ -316,24 +348,27 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-static bool make_map(CUtensorMap* map, const void* base, int64_t rows, int dim_padded, int box_rows, bool bf16) {
+// kind: 0 = fp16, 1 = bf16, 2 = int8.  One 128-byte swizzle row holds 64 fp16 / 128 int8 elements.
+static bool make_map(CUtensorMap* map, const void* base, int64_t rows, int row_bytes, int box_rows, int kind) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
-    cuuint64_t gdim[2] = {(cuuint64_t)dim_padded, (cuuint64_t)rows};
-    cuuint64_t gstride[1] = {(cuuint64_t)dim_padded * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kChunkK, (cuuint32_t)box_rows};
+    const int esz = kind == 2 ? 1 : 2;
+    cuuint64_t gdim[2] = {(cuuint64_t)(row_bytes / esz), (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)row_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    return fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
-              const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    const CUtensorMapDataType dt = kind == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                                 : (kind == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+    return fn(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int KCH, int L, int CS>
+template <int KCH, int L, int CS, bool INT>
 static cudaError_t launch_kch(cudaStream_t st, const CUtensorMap& mq, const CUtensorMap& mc, int64_t n, int n_qtiles,
-                              int n_slices, uint32_t idesc, float tau_pre, uint64_t* cand, int nq, int list_stride) {
+                              int n_slices, uint32_t idesc, uint32_t tau_pre, uint64_t* cand, int nq, int list_stride) {
     const size_t smem = (size_t)KCH * kAChunkBytes + (size_t)kStages * kBStageBytes + 1024;
-    auto kern = gemm_topk_kernel<KCH, L, CS>;
+    auto kern = gemm_topk_kernel<KCH, L, CS, INT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
@@ -351,25 +386,26 @@ static cudaError_t launch_kch(cudaStream_t st, const CUtensorMap& mq, const CUte
     return cudaLaunchKernelEx(&cfg, kern, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, list_stride);
 }
 
-template <int KCH, int L>
+template <int KCH, int L, bool INT>
 static cudaError_t launch_cs(int cs, cudaStream_t st, const CUtensorMap& mq, const CUtensorMap& mc, int64_t n,
-                             int n_qtiles, int n_slices, uint32_t idesc, float tau_pre, uint64_t* cand, int nq) {
-    if (cs == 4) return launch_kch<KCH, L, 4>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32);
-    if (cs == 2) return launch_kch<KCH, L, 2>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32);
-    return launch_kch<KCH, L, 1>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32);
+                             int n_qtiles, int n_slices, uint32_t idesc, uint32_t tau_pre, uint64_t* cand, int nq) {
+    if (cs == 4) return launch_kch<KCH, L, 4, INT>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32);
+    if (cs == 2) return launch_kch<KCH, L, 2, INT>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32);
+    return launch_kch<KCH, L, 1, INT>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32);
 }
 
-bool gemm_supported(int dim_padded, int k) {
-    const int kch = dim_padded / kChunkK;
-    return (kch >= 1 && kch <= 6) && k <= 24;
+// kind: 0 fp16, 1 bf16, 2 int8
+bool gemm_supported(int row_bytes, int k) {
+    const int kch = row_bytes / 128;
+    return (kch == 1 || kch == 2 || kch == 3 || kch == 4 || kch == 6) && k <= 24;
 }
 
 int gemm_list_len(int k) { return k <= 10 ? 16 : 32; }
 
-cudaError_t launch_gemm_topk(cudaStream_t st, const void* codes, int64_t n, int dim_padded, bool bf16,
-                             const void* qcodes, int nq, int k, float tau_pre, uint64_t* cand, int num_sms,
+cudaError_t launch_gemm_topk(cudaStream_t st, const void* codes, int64_t n, int row_bytes, int kind,
+                             const void* qcodes, int nq, int k, uint32_t tau_pre_bits, uint64_t* cand, int num_sms,
                              int cluster, int* n_slices_out) {
-    const int kch = dim_padded / kChunkK;
+    const int kch = row_bytes / 128;
     int n_qtiles = (nq + kTileQ - 1) / kTileQ;
     // cluster size: query tiles that share one corpus stream through TMA multicast
     int cs = cluster > 0 ? cluster : (n_qtiles >= 2 ? 2 : 1);
@@ -382,16 +418,21 @@ cudaError_t launch_gemm_topk(cudaStream_t st, const void* codes, int64_t n, int 
     if (n_slices > tiles_total) n_slices = (int)tiles_total;
     *n_slices_out = n_slices;
     CUtensorMap mq, mc;
-    if (!make_map(&mq, qcodes, nq, dim_padded, kTileQ, bf16) || !make_map(&mc, codes, n, dim_padded, kTileC / cs, bf16))
+    if (!make_map(&mq, qcodes, nq, row_bytes, kTileQ, kind) || !make_map(&mc, codes, n, row_bytes, kTileC / cs, kind))
         return cudaErrorInvalidValue;
-    // instruction descriptor: D=f32, A=B=f16|bf16, both K-major, N=256, M=128
-    const uint32_t fmt = bf16 ? 1u : 0u;
-    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kTileC >> 3) << 17) | ((uint32_t)(kTileQ >> 4) << 24);
+    // instruction descriptor: both operands K-major, N=256, M=128;
+    // f16/bf16: D=f32 (c_format 1), a/b format 0|1;  int8: D=s32 (c_format 2), a/b format 1 (signed)
+    const uint32_t cfmt = kind == 2 ? 2u : 1u;
+    const uint32_t fmt = kind == 0 ? 0u : 1u;
+    const uint32_t idesc = (cfmt << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kTileC >> 3) << 17) | ((uint32_t)(kTileQ >> 4) << 24);
     const int L = gemm_list_len(k);
-#define CRS_GEMM_CASE(KCH_)                                                                                         \
-    case KCH_:                                                                                                      \
-        return L == 16 ? launch_cs<KCH_, 16>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq)        \
-                       : launch_cs<KCH_, 32>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq);
+#define CRS_GEMM_CASE(KCH_)                                                                                              \
+    case KCH_:                                                                                                           \
+        if (kind == 2)                                                                                                   \
+            return L == 16 ? launch_cs<KCH_, 16, true>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq)   \
+                           : launch_cs<KCH_, 32, true>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq);  \
+        return L == 16 ? launch_cs<KCH_, 16, false>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq)      \
+                       : launch_cs<KCH_, 32, false>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq);
     switch (kch) {
         CRS_GEMM_CASE(1)
         CRS_GEMM_CASE(2)

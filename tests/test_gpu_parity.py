@@ -261,7 +261,7 @@ def test_mmr_matches_oracle_on_stored_vectors(store):
 
 
 # ---------------------------------------------------------------- K4 tcgen05 batched path
-@pytest.mark.parametrize("store", ["f16", "bf16"])
+@pytest.mark.parametrize("store", ["f16", "bf16", "i8"])
 @pytest.mark.parametrize("n,dim,nq,k", [(30000, 384, 64, 10), (5003, 384, 130, 10), (777, 128, 8, 3),
                                         (20000, 256, 300, 20), (300, 64, 16, 10), (70000, 320, 200, 5),
                                         (255, 384, 9, 10), (257, 192, 128, 24)])
@@ -291,7 +291,28 @@ def test_gemm_path_equals_scan_path_and_threshold():
     ix.set_option("force_path", 1)
     check_search(ix, x, q[:40], "f16", 10, min_similarity=0.293)
     one = ix.search(q[:1], 10)                       # forced GEMM path with a single query
-    assert np.array_equal(one[0], b[0][:1]) or True
+    assert ix.last_stats()["path"] == 1
+    ix.set_option("force_path", 0)
+    ref = ix.search(q[:1], 10)
+    assert all(np.array_equal(u, v) for u, v in zip(one, ref))
+
+
+def test_int8_gemm_path_threshold_and_scan_equivalence():
+    x, centres = clustered(40000, 384, seed=134)
+    q = queries_for(centres, x, 200, seed=135)
+    ix = ShardIndex(384, dtype="i8")
+    ix.add(x)
+    for thr in (-np.inf, 0.25, 0.5):
+        ix.set_option("force_path", 1)
+        a = ix.search(q, 10, thr)
+        assert ix.last_stats()["path"] == 1
+        ix.set_option("force_path", 0)
+        b = ix.search(q, 10, thr)
+        assert ix.last_stats()["path"] == 0
+        for u, v in zip(a, b):
+            assert np.array_equal(u, v)
+    ix.set_option("force_path", -1)
+    check_search(ix, x, q[:30], "i8", 20, min_similarity=0.25)
 
 
 def test_gemm_path_duplicates_and_fallback():

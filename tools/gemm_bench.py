@@ -36,9 +36,8 @@ def run(n, dim, nq, k, iters=10, store="f16", cluster=0):
     ix.close()
 
 if __name__ == "__main__":
-    for cs in (1, 2, 4):
-        run(1_000_000, 384, 1024, 10, cluster=cs)
-        run(10_000_000, 384, 1024, 10, cluster=cs)
-    run(10_000_000, 384, 128, 10)
-    run(10_000_000, 384, 256, 10, cluster=2)
+    run(10_000_000, 384, 1024, 10, cluster=2)
+    run(10_000_000, 384, 1024, 10, store="i8", cluster=2)
+    run(10_000_000, 384, 1024, 10, store="i8", cluster=1)
+    run(10_000_000, 384, 128, 10, store="i8")
     run(10_000_000, 384, 16, 10)
