@@ -51,7 +51,8 @@ SYMBOLS = {
 
 class SearchStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int32), ("path", C.c_int32), ("grid", C.c_int32),
-                ("list_len", C.c_int32), ("uncertified_total", C.c_int64), ("searches_total", C.c_int64)]
+                ("list_len", C.c_int32), ("uncertified_total", C.c_int64), ("searches_total", C.c_int64),
+                ("max_fast_error", C.c_float), ("reserved", C.c_int32)]
 
 
 def build_library(force: bool = False) -> str:

@@ -106,7 +106,8 @@ struct crs_index {
     DevScratch<uint32_t> ids_dev;
     DevScratch<uint8_t> scores_dev;
     DevScratch<uint32_t> allow_dev;
-    int32_t* n_flagged = nullptr;      // device counters: [0] this search, [1] since create
+    int32_t* n_flagged = nullptr;      // device counters: [0] uncertified this search, [1] since create,
+                                       // [2] float bits of the largest |fast - exact| score seen in finalize
     crs_search_stats stats{};
     int profiling = 0;
     cudaEvent_t evs[32][2] = {};               // ring of event pairs bracketing the dominant kernel(s) of each search
@@ -208,9 +209,9 @@ int crs_index_create(crs_index** out, int dim, crs_dtype store, crs_metric metri
     ix->row_bytes = row_bytes_for(dp, store);
     ix->reserve_hint = reserve_rows;
     ix->num_sms = prop.multiProcessorCount;
-    e = cudaMalloc(&ix->n_flagged, 2 * sizeof(int32_t));
+    e = cudaMalloc(&ix->n_flagged, 4 * sizeof(int32_t));
     if (e != cudaSuccess) { delete ix; return cuda_fail(e, "cudaMalloc"); }
-    cudaMemset(ix->n_flagged, 0, 2 * sizeof(int32_t));
+    cudaMemset(ix->n_flagged, 0, 4 * sizeof(int32_t));
     if (reserve_rows > 0) {
         int rc = grow(ix, reserve_rows);
         if (rc != CRS_OK) { cudaFree(ix->n_flagged); delete ix; return rc; }
@@ -333,8 +334,11 @@ int crs_index_last_stats(const crs_index* ix, crs_search_stats* out) {
     *out = ix->stats;
     int32_t tot = 0;
     DeviceGuard g(ix->device);
-    CRS_CUDA(cudaMemcpy(&tot, ix->n_flagged + 1, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    int32_t cnt[3] = {0, 0, 0};
+    CRS_CUDA(cudaMemcpy(cnt, ix->n_flagged, sizeof(cnt), cudaMemcpyDeviceToHost));
+    tot = cnt[1];
     out->uncertified_total = tot;
+    memcpy(&out->max_fast_error, &cnt[2], sizeof(float));
     return CRS_OK;
 }
 

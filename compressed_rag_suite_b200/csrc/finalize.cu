@@ -90,6 +90,7 @@ finalize_kernel(FinalizeArgs a) {
         if (threadIdx.x < M) {
             const uint64_t fk = fast_keys[threadIdx.x];
             uint64_t ek = 0ull;
+            float err = 0.f;
             if (fk != 0ull) {
                 const uint32_t id = key_id(fk);
                 const int chunks = a.dim_padded / 8;
@@ -97,8 +98,15 @@ finalize_kernel(FinalizeArgs a) {
                 const uint4* qv = reinterpret_cast<const uint4*>(a.qcodes) + (size_t)q * chunks;
                 const float s = a.bf16 ? exact_dot<true>(row, qv, chunks) : exact_dot<false>(row, qv, chunks);
                 if (s >= a.min_similarity) ek = make_key(orderable_f32(s), id);
+                err = fabsf(unorderable_f32(key_ord(fk)) - s);
             }
             exact_keys[threadIdx.x] = ek;
+            // statistic: largest fast-vs-exact score gap seen (evidence for the eps bound)
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) err = fmaxf(err, __shfl_xor_sync(CRS_FULL_MASK, err, off));
+            unsigned* slot = reinterpret_cast<unsigned*>(a.n_flagged + 2);
+            if (lane == 0 && __float_as_uint(err) > *reinterpret_cast<volatile unsigned*>(slot))
+                atomicMax(slot, __float_as_uint(err));
         }
         __syncthreads();
     }

@@ -53,6 +53,9 @@ typedef struct crs_search_stats {
     int32_t list_len;          /* candidates kept per query per CTA (M) */
     int64_t uncertified_total; /* float stores: queries that needed the exact fp64 pass, since create */
     int64_t searches_total;
+    float max_fast_error;      /* float stores: largest |fast score - exact score| of any rescored candidate
+                                  since create (the certification bound eps must stay above it) */
+    int32_t reserved;
 } crs_search_stats;
 
 const char* crs_last_error(void);
