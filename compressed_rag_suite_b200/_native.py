@@ -42,6 +42,8 @@ SYMBOLS = {
     "crs_index_kernel_ms_history": (C.c_int, [_P, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]),
     "crs_index_similarity_scale": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "crs_index_fetch_rows": (C.c_int, [_P, _P, C.c_int, _P]),
+    "crs_index_score_rows": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P]),
+    "crs_select_topk": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "crs_mmr": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_double, _P]),
     "crs_merge_topk": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "crs_index_save": (C.c_int, [_P, C.c_char_p]),

@@ -518,7 +518,8 @@ static int search_impl(crs_index* ix, const void* queries, int nq, int k, float 
             }
             if (need_exact) {
                 CRS_CUDA(crs::launch_exact_scan(st, ix->codes, ix->count, ix->dim_padded, fa.bf16, ix->qcodes.p, nq,
-                                                ix->flags.p, min_similarity, ix->cand.p, plan));
+                                                ix->flags.p, min_similarity, ix->cand.p, plan,
+                                                ix->force_exact ? nullptr : ix->n_flagged));
                 fa.mode = 1; fa.only_flagged = 1;
                 fa.n_lists = n_lists; fa.list_len = M;      // the exact scan writes one full list per CTA
                 CRS_CUDA(crs::launch_finalize(st, fa));
@@ -603,6 +604,57 @@ int crs_index_fetch_rows(crs_index* ix, const uint32_t* ids, int n, void* out_co
         if (d_ids) cudaFree(d_ids);
         if (d_out) cudaFree(d_out);
     }
+    return CRS_OK;
+}
+
+int crs_index_score_rows(crs_index* ix, const void* queries, int nq, const uint32_t* ids, int m, void* out_scores) {
+    if (!ix) return fail(CRS_EINVAL, "index is NULL");
+    if (nq < 0 || m < 0) return fail(CRS_EINVAL, "nq and m must be >= 0");
+    if (nq == 0 || m == 0) return CRS_OK;
+    if (!queries || !ids || !out_scores) return fail(CRS_EINVAL, "NULL buffer");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = ix->stream;
+    const size_t total = (size_t)nq * m;
+    const bool q_dev = is_device_ptr(queries), ids_dev = is_device_ptr(ids), out_dev = is_device_ptr(out_scores);
+    const float* qd = reinterpret_cast<const float*>(queries);
+    if (!q_dev) {
+        CRS_CUDA(ix->qsrc.ensure((size_t)nq * ix->dim));
+        CRS_CUDA(cudaMemcpyAsync(ix->qsrc.p, queries, (size_t)nq * ix->dim * sizeof(float), cudaMemcpyHostToDevice, st));
+        qd = ix->qsrc.p;
+    }
+    CRS_CUDA(ix->qcodes.ensure((size_t)nq * ix->row_bytes));
+    CRS_CUDA(ix->qnorms.ensure((size_t)nq));
+    CRS_CUDA(crs::launch_encode(st, qd, nq, ix->dim, ix->dim_padded, ix->store, ix->metric, ix->i8_scale,
+                                ix->qcodes.p, ix->qnorms.p));
+    const uint32_t* d_ids = ids;
+    if (!ids_dev) {
+        CRS_CUDA(ix->ids_dev.ensure(total));
+        CRS_CUDA(cudaMemcpyAsync(ix->ids_dev.p, ids, total * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        d_ids = ix->ids_dev.p;
+    }
+    void* d_out = out_scores;
+    if (!out_dev) {
+        CRS_CUDA(ix->scores_dev.ensure(total * 4));
+        d_out = ix->scores_dev.p;
+    }
+    CRS_CUDA(crs::launch_score_rows(st, ix->codes, ix->count, ix->row_base, (int)ix->row_bytes, ix->dim, ix->store,
+                                    ix->qcodes.p, d_ids, nq, m, d_out));
+    if (!out_dev) CRS_CUDA(cudaMemcpyAsync(out_scores, d_out, total * 4, cudaMemcpyDeviceToHost, st));
+    if (!q_dev || !ids_dev || !out_dev) CRS_CUDA(cudaStreamSynchronize(st));
+    return CRS_OK;
+}
+
+int crs_select_topk(void* cuda_stream, const uint32_t* ids, const void* scores, int is_int, int nq, int m, int k_out,
+                    uint32_t* out_ids, void* out_scores, int32_t* out_counts) {
+    if (nq < 0 || m <= 0 || k_out <= 0 || k_out > m) return fail(CRS_EINVAL, "bad sizes");
+    if (m > crs::kMaxListLen) return fail(CRS_EINVAL, "m > 128 not supported");
+    if (nq == 0) return CRS_OK;
+    if (!is_device_ptr(ids) || !is_device_ptr(scores) || !is_device_ptr(out_ids) || !is_device_ptr(out_scores) ||
+        !is_device_ptr(out_counts))
+        return fail(CRS_EINVAL, "crs_select_topk takes device buffers");
+    CRS_CUDA(crs::launch_merge_topk(reinterpret_cast<cudaStream_t>(cuda_stream), ids, scores, is_int, 1, nq, m, k_out,
+                                    out_ids, out_scores, out_counts, /*sorted_input=*/false));
     return CRS_OK;
 }
 

@@ -62,7 +62,13 @@ cudaError_t launch_finalize(cudaStream_t st, const FinalizeArgs& a);
 // query; one sorted list per CTA, keys carry the exact fl32 score.
 cudaError_t launch_exact_scan(cudaStream_t st, const void* codes, int64_t n, int dim_padded, bool bf16,
                               const void* qcodes, int nq, const int32_t* flags, float min_similarity,
-                              uint64_t* cand, const ScanPlan& plan);
+                              uint64_t* cand, const ScanPlan& plan,
+                              const int32_t* n_flagged /*device counter; kernel exits at once when it is 0; NULL = always run*/);
+
+// K8: canonical scores of given (query, global row id) pairs; rows of other shards -> -inf / INT32_MIN.
+cudaError_t launch_score_rows(cudaStream_t st, const void* codes, int64_t n_rows, uint32_t row_base, int row_bytes,
+                              int dim, crs_dtype store, const void* qcodes, const uint32_t* ids, int nq, int m,
+                              void* out);
 
 // K4 / K5: tcgen05 Q*C^T with fused top-L epilogue.  kind 0 = fp16, 1 = bf16 (kind::f16, f32
 // accumulate, candidates for finalize mode 0), 2 = int8 (kind::i8, exact int32 scores, finalize
@@ -78,7 +84,7 @@ cudaError_t launch_gemm_topk(cudaStream_t st, const void* codes, int64_t n, int 
 // K7: merge G lists of k_in (id, raw score) per query into the global top k_out.
 cudaError_t launch_merge_topk(cudaStream_t st, const uint32_t* ids, const void* scores, int is_int,
                               int n_lists, int nq, int k_in, int k_out,
-                              uint32_t* out_ids, void* out_scores, int32_t* out_counts);
+                              uint32_t* out_ids, void* out_scores, int32_t* out_counts, bool sorted_input = true);
 
 // K6: greedy MMR over m candidate vectors per query.
 cudaError_t launch_mmr(cudaStream_t st, const void* vecs, crs_dtype store, int dim_padded, int dim,

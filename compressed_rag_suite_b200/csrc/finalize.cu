@@ -200,8 +200,10 @@ template <int LPL, bool BF16>
 __global__ void __launch_bounds__(kExactWarps * 32)
 exact_scan_kernel(const uint4* __restrict__ codes, int64_t n_rows, int chunks, const uint4* __restrict__ qcodes,
                   int nq, const int32_t* __restrict__ flags, float min_similarity, uint64_t* __restrict__ cand,
-                  const uint32_t* __restrict__ allow) {
+                  const uint32_t* __restrict__ allow, const int32_t* __restrict__ n_flagged) {
     constexpr int M = 32 * LPL;
+    // the usual case: finalize certified every query of this search -> nothing to do
+    if (n_flagged != nullptr && *n_flagged == 0) return;
     __shared__ uint64_t stage[kExactWarps * M];
     __shared__ int s_list[1024];
     __shared__ int s_cnt;
@@ -250,18 +252,79 @@ exact_scan_kernel(const uint4* __restrict__ codes, int64_t n_rows, int chunks, c
 
 cudaError_t launch_exact_scan(cudaStream_t st, const void* codes, int64_t n, int dim_padded, bool bf16,
                               const void* qcodes, int nq, const int32_t* flags, float min_similarity,
-                              uint64_t* cand, const ScanPlan& plan) {
+                              uint64_t* cand, const ScanPlan& plan, const int32_t* n_flagged) {
     if (nq <= 0) return cudaSuccess;
     const int chunks = dim_padded / 8;
     const uint4* c = reinterpret_cast<const uint4*>(codes);
     const uint4* qv = reinterpret_cast<const uint4*>(qcodes);
     const int threads = kExactWarps * 32;
     if (plan.lpl == 1) {
-        if (bf16) exact_scan_kernel<1, true><<<plan.grid, threads, 0, st>>>(c, n, chunks, qv, nq, flags, min_similarity, cand, plan.allow);
-        else      exact_scan_kernel<1, false><<<plan.grid, threads, 0, st>>>(c, n, chunks, qv, nq, flags, min_similarity, cand, plan.allow);
+        if (bf16) exact_scan_kernel<1, true><<<plan.grid, threads, 0, st>>>(c, n, chunks, qv, nq, flags, min_similarity, cand, plan.allow, n_flagged);
+        else      exact_scan_kernel<1, false><<<plan.grid, threads, 0, st>>>(c, n, chunks, qv, nq, flags, min_similarity, cand, plan.allow, n_flagged);
     } else {
-        if (bf16) exact_scan_kernel<4, true><<<plan.grid, threads, 0, st>>>(c, n, chunks, qv, nq, flags, min_similarity, cand, plan.allow);
-        else      exact_scan_kernel<4, false><<<plan.grid, threads, 0, st>>>(c, n, chunks, qv, nq, flags, min_similarity, cand, plan.allow);
+        if (bf16) exact_scan_kernel<4, true><<<plan.grid, threads, 0, st>>>(c, n, chunks, qv, nq, flags, min_similarity, cand, plan.allow, n_flagged);
+        else      exact_scan_kernel<4, false><<<plan.grid, threads, 0, st>>>(c, n, chunks, qv, nq, flags, min_similarity, cand, plan.allow, n_flagged);
+    }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ K8: candidate rescoring
+// Canonical score of given (query, row) pairs: fl32 of the fp64-sequential dot for the float
+// stores, exact int32 dot for I8, dim - 2*hamming for B1 — the same values a search on this
+// index reports.  One thread per pair (rows are walked uncoalesced: this is a latency-bound
+// pass over <= 128 candidates per query).  Rows this shard does not own, and pad ids, get the
+// "absent" score (-inf / INT32_MIN) so that a MAX reduction over the shards assembles the row.
+template <int STORE>
+__global__ void __launch_bounds__(128)
+score_rows_kernel(const uint8_t* __restrict__ codes, int64_t n_rows, uint32_t row_base, int row_bytes, int dim,
+                  const uint8_t* __restrict__ qcodes, const uint32_t* __restrict__ ids, int nq, int m,
+                  void* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)nq * m) return;
+    const int q = (int)(i / m);
+    const uint32_t id = ids[i];
+    const int64_t local = (int64_t)id - (int64_t)row_base;
+    const bool have = (id != CRS_PAD_ID) && local >= 0 && local < n_rows;
+    const uint4* row = reinterpret_cast<const uint4*>(codes + (size_t)(have ? local : 0) * row_bytes);
+    const uint4* qv = reinterpret_cast<const uint4*>(qcodes + (size_t)q * row_bytes);
+    const int chunks = row_bytes / 16;
+    if constexpr (STORE == CRS_F16 || STORE == CRS_BF16) {
+        float s = -INFINITY;
+        if (have) s = exact_dot<STORE == CRS_BF16>(row, qv, chunks);
+        reinterpret_cast<float*>(out)[i] = s;
+    } else {
+        int32_t s = INT32_MIN;
+        if (have) {
+            int acc = 0;
+            for (int c = 0; c < chunks; ++c) {
+                const uint4 a = row[c], b = qv[c];
+                if constexpr (STORE == CRS_I8) {
+                    acc = __dp4a((int)a.x, (int)b.x, acc); acc = __dp4a((int)a.y, (int)b.y, acc);
+                    acc = __dp4a((int)a.z, (int)b.z, acc); acc = __dp4a((int)a.w, (int)b.w, acc);
+                } else {
+                    acc += __popc(a.x ^ b.x) + __popc(a.y ^ b.y) + __popc(a.z ^ b.z) + __popc(a.w ^ b.w);
+                }
+            }
+            s = (STORE == CRS_B1) ? dim - 2 * acc : acc;
+        }
+        reinterpret_cast<int32_t*>(out)[i] = s;
+    }
+}
+
+cudaError_t launch_score_rows(cudaStream_t st, const void* codes, int64_t n_rows, uint32_t row_base, int row_bytes,
+                              int dim, crs_dtype store, const void* qcodes, const uint32_t* ids, int nq, int m,
+                              void* out) {
+    const int64_t total = (int64_t)nq * m;
+    if (total <= 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((total + 127) / 128);
+    const uint8_t* c = reinterpret_cast<const uint8_t*>(codes);
+    const uint8_t* qc = reinterpret_cast<const uint8_t*>(qcodes);
+    switch (store) {
+        case CRS_F16:  score_rows_kernel<CRS_F16><<<grid, 128, 0, st>>>(c, n_rows, row_base, row_bytes, dim, qc, ids, nq, m, out); break;
+        case CRS_BF16: score_rows_kernel<CRS_BF16><<<grid, 128, 0, st>>>(c, n_rows, row_base, row_bytes, dim, qc, ids, nq, m, out); break;
+        case CRS_I8:   score_rows_kernel<CRS_I8><<<grid, 128, 0, st>>>(c, n_rows, row_base, row_bytes, dim, qc, ids, nq, m, out); break;
+        case CRS_B1:   score_rows_kernel<CRS_B1><<<grid, 128, 0, st>>>(c, n_rows, row_base, row_bytes, dim, qc, ids, nq, m, out); break;
+        default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
 }

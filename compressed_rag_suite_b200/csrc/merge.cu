@@ -13,7 +13,7 @@ namespace crs {
 
 constexpr int kMergeWarps = 4;
 
-template <int LPL>
+template <int LPL, bool SORT>
 __global__ void __launch_bounds__(kMergeWarps * 32)
 merge_topk_kernel(const uint32_t* __restrict__ ids, const void* __restrict__ scores, int is_int,
                   int n_lists, int nq, int k_in, int k_out,
@@ -41,6 +41,7 @@ merge_topk_kernel(const uint32_t* __restrict__ ids, const void* __restrict__ sco
             }
             b[s] = key;
         }
+        if constexpr (SORT) warp_sort_desc<LPL>(b, lane);     // unsorted candidates (rescored lists)
         warp_merge_desc<LPL>(e, b, lane);
     }
     int nvalid = 0;
@@ -64,12 +65,18 @@ merge_topk_kernel(const uint32_t* __restrict__ ids, const void* __restrict__ sco
 
 cudaError_t launch_merge_topk(cudaStream_t st, const uint32_t* ids, const void* scores, int is_int,
                               int n_lists, int nq, int k_in, int k_out,
-                              uint32_t* out_ids, void* out_scores, int32_t* out_counts) {
+                              uint32_t* out_ids, void* out_scores, int32_t* out_counts, bool sorted_input) {
     if (nq <= 0) return cudaSuccess;
     if (k_in > kMaxListLen || k_out > k_in || k_out <= 0 || n_lists <= 0) return cudaErrorInvalidValue;
     const int grid = (nq + kMergeWarps - 1) / kMergeWarps;
-    if (k_in <= 32) merge_topk_kernel<1><<<grid, kMergeWarps * 32, 0, st>>>(ids, scores, is_int, n_lists, nq, k_in, k_out, out_ids, out_scores, out_counts);
-    else            merge_topk_kernel<4><<<grid, kMergeWarps * 32, 0, st>>>(ids, scores, is_int, n_lists, nq, k_in, k_out, out_ids, out_scores, out_counts);
+    const int threads = kMergeWarps * 32;
+    if (sorted_input) {
+        if (k_in <= 32) merge_topk_kernel<1, false><<<grid, threads, 0, st>>>(ids, scores, is_int, n_lists, nq, k_in, k_out, out_ids, out_scores, out_counts);
+        else            merge_topk_kernel<4, false><<<grid, threads, 0, st>>>(ids, scores, is_int, n_lists, nq, k_in, k_out, out_ids, out_scores, out_counts);
+    } else {
+        if (k_in <= 32) merge_topk_kernel<1, true><<<grid, threads, 0, st>>>(ids, scores, is_int, n_lists, nq, k_in, k_out, out_ids, out_scores, out_counts);
+        else            merge_topk_kernel<4, true><<<grid, threads, 0, st>>>(ids, scores, is_int, n_lists, nq, k_in, k_out, out_ids, out_scores, out_counts);
+    }
     return cudaGetLastError();
 }
 

@@ -184,6 +184,60 @@ class ShardIndex:
                                                out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def fetch_rows_device(self, ids, out=None):
+        """Device form of fetch_rows: ids int32 CUDA tensor (uint32 bit patterns) of any shape ->
+        uint8 CUDA tensor ids.shape + (row_bytes,); rows of other shards stay as they are in `out`
+        (zeros by default).  Enqueued on the current stream."""
+        import torch
+        ids = ids.contiguous()
+        if out is None:
+            out = torch.zeros(tuple(ids.shape) + (self.row_bytes,), dtype=torch.uint8, device=ids.device)
+        self._use_torch_stream()
+        N.check(self._lib.crs_index_fetch_rows(self._h, C.c_void_p(ids.data_ptr()), ids.numel(),
+                                               C.c_void_p(out.data_ptr())))
+        return out
+
+    def score_rows(self, queries, ids):
+        """K8: canonical score of every (query q, row ids[q, j]) pair on this shard.
+        queries [nq, dim] float32, ids [nq, m] (numpy uint32 or torch CUDA int32 bit patterns)
+        -> [nq, m] float32 | int32; rows this shard does not hold -> -inf / INT32_MIN."""
+        if _is_torch_cuda(queries):
+            import torch
+            q = queries.contiguous()
+            ids = ids.contiguous()
+            nq, m = ids.shape
+            out = torch.empty((nq, m), dtype=torch.int32 if self.is_int else torch.float32, device=q.device)
+            self._use_torch_stream()
+            N.check(self._lib.crs_index_score_rows(self._h, C.c_void_p(q.data_ptr()), nq, C.c_void_p(ids.data_ptr()), m,
+                                                   C.c_void_p(out.data_ptr())))
+            return out
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        i = np.ascontiguousarray(ids, dtype=np.uint32)
+        if i.ndim == 1:
+            i = i[None, :]
+        if q.shape[1] != self.dim or i.shape[0] != q.shape[0]:
+            raise ValueError(f"queries must be [nq, {self.dim}] and ids [nq, m]")
+        nq, m = i.shape
+        out = np.empty((nq, m), dtype=np.int32 if self.is_int else np.float32)
+        N.check(self._lib.crs_index_score_rows(self._h, q.ctypes.data_as(C.c_void_p), nq, i.ctypes.data_as(C.c_void_p), m,
+                                               out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def mmr_device(self, vecs, relevance, lam: float, k_out: int):
+        """Device form of mmr: vecs uint8 CUDA [nq, m, row_bytes], relevance float64 CUDA [nq, m]
+        -> int32 CUDA [nq, k_out]; enqueued on the current stream."""
+        import torch
+        v = vecs.contiguous()
+        r = relevance.contiguous()
+        nq, m = r.shape
+        out = torch.empty((nq, int(k_out)), dtype=torch.int32, device=v.device)
+        self._use_torch_stream()
+        N.check(self._lib.crs_mmr(self._h, C.c_void_p(v.data_ptr()), C.c_void_p(r.data_ptr()), nq, m, int(k_out),
+                                  float(lam), C.c_void_p(out.data_ptr())))
+        return out
+
     def mmr(self, vecs: np.ndarray, relevance, lam: float, k_out: Optional[int] = None) -> np.ndarray:
         """Greedy MMR order.  vecs: [nq, m, row_bytes] uint8 stored codes (or [m, row_bytes]);
         relevance: [nq, m] float64.  -> int32 [nq, k_out] positions."""
@@ -210,6 +264,24 @@ class ShardIndex:
         h = C.c_void_p()
         N.check(lib.crs_index_load(C.byref(h), path.encode(), int(device), int(row_base)))
         return cls(0, device=device, row_base=row_base, _handle=h)
+
+
+def select_topk(ids, scores, k_out: int):
+    """Order UNSORTED candidates (torch CUDA: ids int32 bit patterns [nq, m], scores f32|i32 [nq, m])
+    by (score desc, id asc) -> (ids [nq,k_out], scores [nq,k_out], counts [nq]); pad ids skipped."""
+    import torch
+    nq, m = ids.shape
+    ids = ids.contiguous()
+    scores = scores.contiguous()
+    is_int = scores.dtype == torch.int32
+    out_ids = torch.empty((nq, k_out), dtype=torch.int32, device=ids.device)
+    out_sc = torch.empty((nq, k_out), dtype=scores.dtype, device=ids.device)
+    out_cnt = torch.empty((nq,), dtype=torch.int32, device=ids.device)
+    st = torch.cuda.current_stream(ids.device).cuda_stream
+    N.check(N.lib().crs_select_topk(C.c_void_p(st), C.c_void_p(ids.data_ptr()), C.c_void_p(scores.data_ptr()),
+                                    int(is_int), nq, m, int(k_out), C.c_void_p(out_ids.data_ptr()),
+                                    C.c_void_p(out_sc.data_ptr()), C.c_void_p(out_cnt.data_ptr())))
+    return out_ids, out_sc, out_cnt
 
 
 def merge_topk(ids, scores, k_out: int):

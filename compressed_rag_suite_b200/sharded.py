@@ -15,6 +15,8 @@ from __future__ import annotations
 import math
 from typing import Tuple
 
+import numpy as np
+
 
 def shard_bounds(n_total: int, world: int, rank: int) -> Tuple[int, int]:
     """Contiguous block of rows owned by `rank`: [lo, hi)."""
@@ -74,3 +76,85 @@ class ShardedSearcher:
         g_ids, g_sc = unpack_candidates(gathered, self.index.is_int)
         self.merge_launches = 1
         return merge_topk(g_ids, g_sc, k)
+
+
+# ------------------------------------------------------------------------------------------
+# Candidate-set steps that follow the sharded top-k (BASELINE configs 4 and 5)
+
+def assemble_over_shards(t, group=None):
+    """Every rank contributed its own rows of `t` and the neutral element elsewhere (0 bytes for
+    stored codes, -inf / INT32_MIN for scores): an elementwise MAX over the ranks assembles the
+    full tensor on every rank.  In place; no-op without a process group."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return t
+
+
+def reference_relevance(sims):
+    """The reference's `score` of a hit from its cosine similarity, in float64 exactly as Python
+    evaluates it: Chroma distance d = 1 - cos (rag/indexing.py:171-176), then
+    rag/retrieval.py:75-77: d <- clamp(d, 0, 2); score = clamp(1 - d*d/2, 0, 1)."""
+    import torch
+    d = 1.0 - sims.to(torch.float64)
+    d = torch.clamp(d, 0.0, 2.0)
+    return torch.clamp(1.0 - (d * d / 2.0), 0.0, 1.0)
+
+
+def similarity_of(index, raw):
+    """raw scores (torch) -> float32 cosine-domain similarity, same arithmetic as ShardIndex.similarity."""
+    import torch
+    if index.dtype == "i8":
+        return raw.to(torch.float32) * float(np.float32(index.similarity_scale))
+    if index.dtype == "b1":
+        return (raw.to(torch.float64) / float(index.dim)).to(torch.float32)
+    return raw.to(torch.float32)
+
+
+class ShardedMMRSearcher(ShardedSearcher):
+    """BASELINE config 4: global top-`fetch_k` over the row shards, then the reference's greedy MMR
+    (rag/retrieval.py:219-277) over the STORED vectors of those candidates, first `k` of the
+    greedy order.  Candidate vectors are gathered by their owners and assembled with one MAX
+    all-reduce of [nq, fetch_k, row_bytes] bytes (38 KB per query at 100 x 384 int8)."""
+
+    def search_mmr(self, queries, k: int, fetch_k: int, diversity_penalty: float,
+                   min_similarity: float = -math.inf):
+        """-> (ids int32 [nq,k] (pad -1), similarity f32 [nq,k], relevance f64 [nq,k], counts [nq])."""
+        import torch
+        ids, raw, cnt = self.search(queries, fetch_k, min_similarity)
+        vecs = assemble_over_shards(self.index.fetch_rows_device(ids), self.group)
+        sims = similarity_of(self.index, raw)
+        valid = torch.arange(fetch_k, device=ids.device)[None, :] < cnt[:, None]
+        rel = torch.where(valid, reference_relevance(sims), torch.full_like(sims, -math.inf, dtype=torch.float64))
+        order = self.index.mmr_device(vecs, rel, 1.0 - diversity_penalty, k)            # [nq, k], -1 = none
+        ok = order >= 0
+        pos = order.clamp(min=0).to(torch.int64)
+        out_ids = torch.where(ok, torch.gather(ids, 1, pos), torch.full_like(order, -1))
+        out_sims = torch.where(ok, torch.gather(sims, 1, pos), torch.full_like(sims[:, :k], -math.inf))
+        out_rel = torch.where(ok, torch.gather(rel, 1, pos), torch.full_like(rel[:, :k], -math.inf))
+        return out_ids, out_sims, out_rel, ok.sum(dim=1).to(torch.int32)
+
+
+class TwoStageSearcher:
+    """BASELINE config 5: a coarse index (1-bit codes, Hamming) picks the global top-`fetch_k`,
+    a fine index over the SAME rows (fp16) rescores those candidates with its canonical score
+    (K8, crs_index_score_rows) and the best `k` by (fine score desc, id asc) are returned.
+    Both indexes are row-sharded identically; per search: one allgather of the coarse
+    candidates + one MAX all-reduce of [nq, fetch_k] fine scores."""
+
+    def __init__(self, coarse, fine, group=None):
+        if len(coarse) != len(fine) or coarse.row_base != fine.row_base:
+            raise ValueError("coarse and fine index must hold the same rows")
+        self.coarse = ShardedSearcher(coarse, group)
+        self.fine = fine
+        self.group = group
+
+    def search(self, queries, k: int, fetch_k: int, min_similarity: float = -math.inf):
+        """-> (ids int32 [nq,k] (uint32 bit patterns, pad -1), fine scores f32 [nq,k], counts [nq])."""
+        import torch
+        from .index import select_topk
+        ids, _, _ = self.coarse.search(queries, fetch_k)
+        fine = assemble_over_shards(self.fine.score_rows(queries, ids), self.group)
+        if min_similarity > -math.inf:
+            ids = torch.where(fine >= min_similarity, ids, torch.full_like(ids, -1))
+        return select_topk(ids, fine, k)

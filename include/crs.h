@@ -121,6 +121,21 @@ int crs_index_similarity_scale(const crs_index* idx, double* out_scale);
  * shard are skipped (their output rows are left untouched).  Feeds crs_mmr. */
 int crs_index_fetch_rows(crs_index* idx, const uint32_t* ids, int n, void* out_codes);
 
+/* K8, candidate rescoring (no reference counterpart: BASELINE config 5, "Hamming top-100 with
+ * fp16 rescoring of candidates"; also how a coarse index of one store dtype is refined by a
+ * finer one).  Canonical score — the value crs_index_search reports for that row — of every
+ * (query q, row ids[q][j]) pair:
+ *   queries    : [nq, dim] fp32, host or device
+ *   ids        : [nq, m] global row ids (CRS_PAD_ID allowed), host or device
+ *   out_scores : [nq, m] float32 (F16/BF16) or int32 (I8/B1); rows this shard does not hold
+ *                and pad ids get -inf / INT32_MIN, so a MAX over shards assembles the result */
+int crs_index_score_rows(crs_index* idx, const void* queries, int nq, const uint32_t* ids, int m,
+                         void* out_scores);
+/* orders UNSORTED candidates (e.g. rescored ones) by (score desc, id asc) and keeps k_out:
+ *   ids/scores : [nq, m] device pointers, m <= 128; pad ids are skipped */
+int crs_select_topk(void* cuda_stream, const uint32_t* ids, const void* scores, int is_int,
+                    int nq, int m, int k_out, uint32_t* out_ids, void* out_scores, int32_t* out_counts);
+
 /* replaces ContextRetriever._apply_diversity — rag/retrieval.py:219-277 — on stored
  * vectors instead of re-embedded texts.
  *   vecs      : [nq, m, row_bytes] stored codes of the m candidates (position order)
