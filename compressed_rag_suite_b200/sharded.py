@@ -57,11 +57,13 @@ def exchange_candidates(packed, group=None):
 class ShardedSearcher:
     """Wraps this rank's ShardIndex; ``search`` returns the GLOBAL top-k on every rank."""
 
-    def __init__(self, index, group=None):
+    def __init__(self, index, group=None, local_only: bool = False):
+        """local_only: the index holds the whole corpus; never exchange (even inside a process group)."""
         import torch.distributed as dist
         self.index = index
         self.group = group
-        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.local_only = local_only
+        self.world = 1 if local_only else (dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1)
         self.merge_launches = 0
 
     def search(self, queries, k: int, min_similarity: float = -math.inf):
@@ -122,7 +124,9 @@ class ShardedMMRSearcher(ShardedSearcher):
         """-> (ids int32 [nq,k] (pad -1), similarity f32 [nq,k], relevance f64 [nq,k], counts [nq])."""
         import torch
         ids, raw, cnt = self.search(queries, fetch_k, min_similarity)
-        vecs = assemble_over_shards(self.index.fetch_rows_device(ids), self.group)
+        vecs = self.index.fetch_rows_device(ids)
+        if self.world > 1:
+            vecs = assemble_over_shards(vecs, self.group)
         sims = similarity_of(self.index, raw)
         valid = torch.arange(fetch_k, device=ids.device)[None, :] < cnt[:, None]
         rel = torch.where(valid, reference_relevance(sims), torch.full_like(sims, -math.inf, dtype=torch.float64))
@@ -142,10 +146,10 @@ class TwoStageSearcher:
     Both indexes are row-sharded identically; per search: one allgather of the coarse
     candidates + one MAX all-reduce of [nq, fetch_k] fine scores."""
 
-    def __init__(self, coarse, fine, group=None):
+    def __init__(self, coarse, fine, group=None, local_only: bool = False):
         if len(coarse) != len(fine) or coarse.row_base != fine.row_base:
             raise ValueError("coarse and fine index must hold the same rows")
-        self.coarse = ShardedSearcher(coarse, group)
+        self.coarse = ShardedSearcher(coarse, group, local_only)
         self.fine = fine
         self.group = group
 
@@ -154,7 +158,9 @@ class TwoStageSearcher:
         import torch
         from .index import select_topk
         ids, _, _ = self.coarse.search(queries, fetch_k)
-        fine = assemble_over_shards(self.fine.score_rows(queries, ids), self.group)
+        fine = self.fine.score_rows(queries, ids)
+        if self.coarse.world > 1:
+            fine = assemble_over_shards(fine, self.group)
         if min_similarity > -math.inf:
             ids = torch.where(fine >= min_similarity, ids, torch.full_like(ids, -1))
         return select_topk(ids, fine, k)
