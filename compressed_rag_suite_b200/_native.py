@@ -43,6 +43,7 @@ SYMBOLS = {
     "crs_index_similarity_scale": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "crs_index_fetch_rows": (C.c_int, [_P, _P, C.c_int, _P]),
     "crs_index_score_rows": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P]),
+    "crs_index_score_vectors": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P]),
     "crs_select_topk": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "crs_mmr": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_double, _P]),
     "crs_merge_topk": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),

@@ -100,7 +100,7 @@ struct crs_index {
     double eps_scale = 1.0;
     // scratch
     DevScratch<float> qsrc, qnorms, norms_tmp;
-    DevScratch<uint8_t> qcodes, stage_rows;
+    DevScratch<uint8_t> qcodes, stage_rows, vec_codes;
     DevScratch<uint64_t> cand;
     DevScratch<int32_t> flags, counts_dev;
     DevScratch<uint32_t> ids_dev;
@@ -229,7 +229,7 @@ int crs_index_destroy(crs_index* ix) {
         if (ix->n_flagged) cudaFree(ix->n_flagged);
         for (auto& p : ix->evs) { if (p[0]) cudaEventDestroy(p[0]); if (p[1]) cudaEventDestroy(p[1]); }
         ix->qsrc.release(); ix->qnorms.release(); ix->norms_tmp.release(); ix->qcodes.release();
-        ix->stage_rows.release(); ix->cand.release(); ix->flags.release(); ix->counts_dev.release();
+        ix->stage_rows.release(); ix->vec_codes.release(); ix->cand.release(); ix->flags.release(); ix->counts_dev.release();
         ix->ids_dev.release(); ix->scores_dev.release(); ix->allow_dev.release();
     }
     delete ix;
@@ -642,6 +642,48 @@ int crs_index_score_rows(crs_index* ix, const void* queries, int nq, const uint3
                                     ix->qcodes.p, d_ids, nq, m, d_out));
     if (!out_dev) CRS_CUDA(cudaMemcpyAsync(out_scores, d_out, total * 4, cudaMemcpyDeviceToHost, st));
     if (!q_dev || !ids_dev || !out_dev) CRS_CUDA(cudaStreamSynchronize(st));
+    return CRS_OK;
+}
+
+int crs_index_score_vectors(crs_index* ix, const void* queries, int nq, const void* rows, int m, void* out_scores) {
+    if (!ix) return fail(CRS_EINVAL, "index is NULL");
+    if (nq < 0 || m < 0) return fail(CRS_EINVAL, "nq and m must be >= 0");
+    if (nq == 0 || m == 0) return CRS_OK;
+    if (!queries || !rows || !out_scores) return fail(CRS_EINVAL, "NULL buffer");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = ix->stream;
+    const size_t total = (size_t)nq * m;
+    const bool q_dev = is_device_ptr(queries), r_dev = is_device_ptr(rows), out_dev = is_device_ptr(out_scores);
+    const float* qd = reinterpret_cast<const float*>(queries);
+    if (!q_dev) {
+        CRS_CUDA(ix->qsrc.ensure((size_t)nq * ix->dim));
+        CRS_CUDA(cudaMemcpyAsync(ix->qsrc.p, queries, (size_t)nq * ix->dim * sizeof(float), cudaMemcpyHostToDevice, st));
+        qd = ix->qsrc.p;
+    }
+    CRS_CUDA(ix->qcodes.ensure((size_t)nq * ix->row_bytes));
+    CRS_CUDA(ix->qnorms.ensure((size_t)nq));
+    CRS_CUDA(crs::launch_encode(st, qd, nq, ix->dim, ix->dim_padded, ix->store, ix->metric, ix->i8_scale,
+                                ix->qcodes.p, ix->qnorms.p));
+    const float* rd = reinterpret_cast<const float*>(rows);
+    if (!r_dev) {
+        CRS_CUDA(ix->stage_rows.ensure(total * ix->dim * sizeof(float)));
+        CRS_CUDA(cudaMemcpyAsync(ix->stage_rows.p, rows, total * ix->dim * sizeof(float), cudaMemcpyHostToDevice, st));
+        rd = reinterpret_cast<const float*>(ix->stage_rows.p);
+    }
+    // the candidate rows go through the same encoder as stored rows, into scratch
+    CRS_CUDA(ix->vec_codes.ensure(total * ix->row_bytes));
+    CRS_CUDA(crs::launch_encode(st, rd, (int64_t)total, ix->dim, ix->dim_padded, ix->store, ix->metric, ix->i8_scale,
+                                ix->vec_codes.p, nullptr));
+    void* d_out = out_scores;
+    if (!out_dev) {
+        CRS_CUDA(ix->scores_dev.ensure(total * 4));
+        d_out = ix->scores_dev.p;
+    }
+    CRS_CUDA(crs::launch_score_rows(st, ix->vec_codes.p, (int64_t)total, 0, (int)ix->row_bytes, ix->dim, ix->store,
+                                    ix->qcodes.p, nullptr, nq, m, d_out));
+    if (!out_dev) CRS_CUDA(cudaMemcpyAsync(out_scores, d_out, total * 4, cudaMemcpyDeviceToHost, st));
+    if (!q_dev || !r_dev || !out_dev) CRS_CUDA(cudaStreamSynchronize(st));
     return CRS_OK;
 }
 

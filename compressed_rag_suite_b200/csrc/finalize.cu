@@ -274,6 +274,7 @@ cudaError_t launch_exact_scan(cudaStream_t st, const void* codes, int64_t n, int
 // index reports.  One thread per pair (rows are walked uncoalesced: this is a latency-bound
 // pass over <= 128 candidates per query).  Rows this shard does not own, and pad ids, get the
 // "absent" score (-inf / INT32_MIN) so that a MAX reduction over the shards assembles the row.
+// ids == NULL: `codes` holds the nq*m candidate rows themselves ([nq][m], freshly encoded).
 template <int STORE>
 __global__ void __launch_bounds__(128)
 score_rows_kernel(const uint8_t* __restrict__ codes, int64_t n_rows, uint32_t row_base, int row_bytes, int dim,
@@ -282,7 +283,7 @@ score_rows_kernel(const uint8_t* __restrict__ codes, int64_t n_rows, uint32_t ro
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)nq * m) return;
     const int q = (int)(i / m);
-    const uint32_t id = ids[i];
+    const uint32_t id = ids ? ids[i] : (uint32_t)i + row_base;      // NULL ids: pair i scores row i of `codes`
     const int64_t local = (int64_t)id - (int64_t)row_base;
     const bool have = (id != CRS_PAD_ID) && local >= 0 && local < n_rows;
     const uint4* row = reinterpret_cast<const uint4*>(codes + (size_t)(have ? local : 0) * row_bytes);

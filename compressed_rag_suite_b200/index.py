@@ -225,6 +225,33 @@ class ShardIndex:
                                                out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def score_vectors(self, queries, rows):
+        """K8 on caller-supplied candidate vectors: queries [nq, dim], rows [nq, m, dim] float32
+        (both numpy or both torch CUDA) -> canonical scores [nq, m] of this index's store dtype."""
+        if _is_torch_cuda(queries):
+            import torch
+            q = queries.contiguous()
+            r = rows.contiguous()
+            nq, m = r.shape[0], r.shape[1]
+            if r.dtype != torch.float32 or r.shape[2] != self.dim or q.shape[0] != nq:
+                raise ValueError(f"rows must be float32 [nq, m, {self.dim}]")
+            out = torch.empty((nq, m), dtype=torch.int32 if self.is_int else torch.float32, device=q.device)
+            self._use_torch_stream()
+            N.check(self._lib.crs_index_score_vectors(self._h, C.c_void_p(q.data_ptr()), nq, C.c_void_p(r.data_ptr()), m,
+                                                      C.c_void_p(out.data_ptr())))
+            return out
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        r = np.ascontiguousarray(rows, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        if r.ndim != 3 or r.shape[2] != self.dim or r.shape[0] != q.shape[0]:
+            raise ValueError(f"rows must be float32 [nq, m, {self.dim}]")
+        nq, m = r.shape[0], r.shape[1]
+        out = np.empty((nq, m), dtype=np.int32 if self.is_int else np.float32)
+        N.check(self._lib.crs_index_score_vectors(self._h, q.ctypes.data_as(C.c_void_p), nq, r.ctypes.data_as(C.c_void_p), m,
+                                                  out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def mmr_device(self, vecs, relevance, lam: float, k_out: int):
         """Device form of mmr: vecs uint8 CUDA [nq, m, row_bytes], relevance float64 CUDA [nq, m]
         -> int32 CUDA [nq, k_out]; enqueued on the current stream."""

@@ -146,21 +146,31 @@ class TwoStageSearcher:
     Both indexes are row-sharded identically; per search: one allgather of the coarse
     candidates + one MAX all-reduce of [nq, fetch_k] fine scores."""
 
-    def __init__(self, coarse, fine, group=None, local_only: bool = False):
-        if len(coarse) != len(fine) or coarse.row_base != fine.row_base:
+    def __init__(self, coarse, fine, group=None, local_only: bool = False, row_source=None):
+        """row_source: optional callable ids (int32 CUDA [nq, m], uint32 bit patterns, pad -1) ->
+        float32 CUDA [nq, m, dim], the candidates' ORIGINAL vectors, for corpora whose fine rows
+        are not resident in HBM (1 B x 1024-d fp16 = 2 TB: re-materialised from the generator, or
+        read from host memory); `fine` then only carries dim / dtype / metric and stays empty.
+        Every rank must be able to produce every candidate (no second collective)."""
+        if row_source is None and (len(coarse) != len(fine) or coarse.row_base != fine.row_base):
             raise ValueError("coarse and fine index must hold the same rows")
         self.coarse = ShardedSearcher(coarse, group, local_only)
         self.fine = fine
         self.group = group
+        self.row_source = row_source
 
     def search(self, queries, k: int, fetch_k: int, min_similarity: float = -math.inf):
         """-> (ids int32 [nq,k] (uint32 bit patterns, pad -1), fine scores f32 [nq,k], counts [nq])."""
         import torch
         from .index import select_topk
         ids, _, _ = self.coarse.search(queries, fetch_k)
-        fine = self.fine.score_rows(queries, ids)
-        if self.coarse.world > 1:
-            fine = assemble_over_shards(fine, self.group)
+        if self.row_source is not None:
+            fine = self.fine.score_vectors(queries, self.row_source(ids))
+            fine = torch.where(ids != -1, fine, torch.full_like(fine, -math.inf))
+        else:
+            fine = self.fine.score_rows(queries, ids)
+            if self.coarse.world > 1:
+                fine = assemble_over_shards(fine, self.group)
         if min_similarity > -math.inf:
             ids = torch.where(fine >= min_similarity, ids, torch.full_like(ids, -1))
         return select_topk(ids, fine, k)

@@ -131,6 +131,13 @@ int crs_index_fetch_rows(crs_index* idx, const uint32_t* ids, int n, void* out_c
  *                and pad ids get -inf / INT32_MIN, so a MAX over shards assembles the result */
 int crs_index_score_rows(crs_index* idx, const void* queries, int nq, const uint32_t* ids, int m,
                          void* out_scores);
+/* the same for candidate vectors the CALLER supplies instead of stored rows (BASELINE config 5 at
+ * full size: the fp16 originals of 1 B x 1024-d rows do not fit in HBM, so the candidates'
+ * fp32 vectors are re-materialised or read from host memory): the rows go through this index's
+ * encoder (normalise + round to the store dtype) and are scored canonically.
+ *   rows : [nq, m, dim] fp32, host or device;  out_scores : [nq, m] */
+int crs_index_score_vectors(crs_index* idx, const void* queries, int nq, const void* rows, int m,
+                            void* out_scores);
 /* orders UNSORTED candidates (e.g. rescored ones) by (score desc, id asc) and keeps k_out:
  *   ids/scores : [nq, m] device pointers, m <= 128; pad ids are skipped */
 int crs_select_topk(void* cuda_stream, const uint32_t* ids, const void* scores, int is_int,

@@ -153,3 +153,34 @@ def test_mmr_pipeline_with_threshold_and_short_lists():
         assert ids[i, :len(w_ids)].tolist() == w_ids
         assert (ids[i, len(w_ids):] == -1).all()
     assert min(lens) < 10, "some query must have fewer than k survivors"
+
+
+@pytest.mark.parametrize("store", ["f16", "bf16", "i8", "b1"])
+def test_score_vectors_equals_score_of_stored_rows(store):
+    """Caller-supplied candidate vectors go through the same encoder -> same canonical scores."""
+    x, centres = clustered(3000, 384, seed=340)
+    q = queries_for(centres, x, 6, seed=341)
+    ix = ShardIndex(384, dtype=store)
+    ix.add(x)
+    ids, raw, cnt = ix.search(q, 40)
+    rows = x[ids.astype(np.int64)]                                   # [nq, 40, 384] original fp32 vectors
+    empty = ShardIndex(384, dtype=store)                             # carries dim / dtype / metric only
+    got = empty.score_vectors(q, rows)
+    assert np.array_equal(got.view(np.uint32), raw.view(np.uint32))
+    gd = empty.score_vectors(torch.from_numpy(q).cuda(), torch.from_numpy(rows).cuda())
+    assert np.array_equal(gd.cpu().numpy().view(np.uint32), raw.view(np.uint32))
+
+
+def test_two_stage_with_rematerialised_rows_equals_resident_fine_index():
+    dim, n = 1024, 12000
+    x, centres = clustered(n, dim, seed=350)
+    q = torch.from_numpy(queries_for(centres, x, 8, seed=351)).cuda()
+    c, f = ShardIndex(dim, dtype="b1"), ShardIndex(dim, dtype="f16")
+    c.add(x); f.add(x)
+    want = TwoStageSearcher(c, f).search(q, 10, 100)
+    xd = torch.from_numpy(x).cuda()
+    src = lambda ids: xd[ids.clamp(min=0).to(torch.int64)]          # noqa: E731  (pad ids -> any row, masked later)
+    got = TwoStageSearcher(c, ShardIndex(dim, dtype="f16"), row_source=src).search(q, 10, 100)
+    for u, v in zip(got, want):
+        assert torch.equal(u.view(torch.int32) if u.dtype == torch.float32 else u,
+                           v.view(torch.int32) if v.dtype == torch.float32 else v)
