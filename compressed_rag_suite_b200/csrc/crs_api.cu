@@ -97,6 +97,7 @@ struct crs_index {
     int force_path = -1;
     int force_exact = 0;
     int gemm_cluster = 0;
+    int gemm_min_nq = 8;        // batches of at least this many queries take the tensor-core path
     double eps_scale = 1.0;
     // scratch
     DevScratch<float> qsrc, qnorms, norms_tmp;
@@ -249,6 +250,7 @@ int crs_index_set_option(crs_index* ix, const char* name, int64_t value) {
     if (!strcmp(name, "force_path")) ix->force_path = (int)value;
     else if (!strcmp(name, "force_exact")) ix->force_exact = (int)value;
     else if (!strcmp(name, "gemm_cluster")) ix->gemm_cluster = (int)value;
+    else if (!strcmp(name, "gemm_min_nq")) ix->gemm_min_nq = (int)value;
     else if (!strcmp(name, "eps_scale")) ix->eps_scale = (double)value / 1000.0;
     else if (!strcmp(name, "profiling")) {
         DeviceGuard g(ix->device);
@@ -382,10 +384,10 @@ static int search_impl(crs_index* ix, const void* queries, int nq, int k, float 
     int lpl;
     if (is_float) { if (k <= 16) lpl = 1; else if (k <= 112) lpl = 4; else return fail(CRS_EINVAL, "k > 112 not supported for float stores"); }
     else { if (k <= 32) lpl = 1; else if (k <= 128) lpl = 4; else return fail(CRS_EINVAL, "k > 128 not supported"); }
-    // batches go to the tcgen05 contraction (K4); single queries / unsupported shapes stream-scan (K1)
-    const bool use_gemm = (is_float || ix->store == CRS_I8) && allow_bits == nullptr && ix->force_path != 0 &&
-                          crs::gemm_supported((int)ix->row_bytes, k) && (ix->force_path == 1 || nq >= 8);
-    if (use_gemm) lpl = 1;
+    // batches go to the tcgen05 contraction (K4/K5); single queries / unsupported shapes stream-scan (K1-K3)
+    const bool use_gemm = (is_float || ix->store == CRS_I8) && ix->force_path != 0 &&
+                          crs::gemm_supported((int)ix->row_bytes, k) && (ix->force_path == 1 || nq >= ix->gemm_min_nq);
+    if (use_gemm && is_float) lpl = (k <= 24) ? 1 : 4;     // slice lists hold 16 / 32 keys: M = 32 covers k <= 24
     const int M = 32 * lpl;
 
     std::lock_guard<std::mutex> lk(ix->mu);
@@ -453,7 +455,7 @@ static int search_impl(crs_index* ix, const void* queries, int nq, int k, float 
         CRS_CUDA(ix->flags.ensure((size_t)nq));
 
         crs::FinalizeArgs fa{};
-        fa.cand = ix->cand.p; fa.n_lists = n_lists; fa.list_len = M; fa.lpl = lpl; fa.nq = nq; fa.k = k;
+        fa.cand = ix->cand.p; fa.n_lists = n_lists; fa.list_len = M; fa.list_stride = M; fa.lpl = lpl; fa.nq = nq; fa.k = k;
         fa.codes = ix->codes; fa.qcodes = ix->qcodes.p; fa.qnorms = ix->qnorms.p;
         fa.dim_padded = ix->dim_padded; fa.bf16 = ix->store == CRS_BF16;
         fa.row_norm_bound = ix->row_norm_bound;
@@ -462,45 +464,61 @@ static int search_impl(crs_index* ix, const void* queries, int nq, int k, float 
         fa.flags = ix->flags.p; fa.n_flagged = ix->n_flagged; fa.is_int = is_int;
 
         ix->stats.path = 0; ix->stats.grid = plan.grid; ix->stats.list_len = M;
-        if (is_float) {
-            // error bound of the fp32 scan score (any summation order): Dp * 2^-24 * |q| * |c|
-            const float eps_rel = (float)((double)ix->dim_padded * ldexp(1.0, -24) * 1.01 * ix->eps_scale);
-            fa.eps_rel = eps_rel;
-            bool need_exact = ix->force_exact != 0;
-            if (!need_exact) {
+        const int32_t min_raw = is_int ? min_raw_for(ix, min_similarity) : 0;
+        bool need_exact = is_float && ix->force_exact != 0;      // test hook: skip the fast pass
+        bool certifying = false;                                  // the fast pass can flag queries for the exact pass
+
+        if (!need_exact) {
+            // ---- fast pass: candidate lists
+            float tau_pre = -INFINITY;
+            if (is_float) {
+                // error bound of the fp32 scan score (any summation order): Dp * 2^-24 * |q| * |c|;
+                // tensor-core accumulation may truncate instead of round: one ulp per term
+                fa.eps_rel = (float)((double)ix->dim_padded * ldexp(1.0, use_gemm ? -23 : -24) * (use_gemm ? 1.05 : 1.01) *
+                                     ix->eps_scale);
                 // cosine queries are unit rows (|q| <= 1.0039); for ip the norm is only known on the
                 // device, so the pre-filter is left off and the threshold applied on the exact score.
-                float tau_pre = -INFINITY;
                 if (ix->metric == CRS_COSINE && min_similarity > -INFINITY)
-                    tau_pre = min_similarity - eps_rel * 1.00390625f * ix->row_norm_bound;
-                if (ix->profiling) CRS_CUDA(cudaEventRecord(ix->evs[ix->ev_count % 32][0], st));
-                if (use_gemm) {
-                    // tensor-core accumulation may truncate instead of round: allow one ulp per term
-                    fa.eps_rel = (float)((double)ix->dim_padded * ldexp(1.0, -23) * 1.05 * ix->eps_scale);
-                    if (tau_pre > -INFINITY)
-                        tau_pre = min_similarity - fa.eps_rel * 1.00390625f * ix->row_norm_bound;
-                    int n_slices = 0;
-                    uint32_t tau_bits;
-                    memcpy(&tau_bits, &tau_pre, sizeof(tau_bits));
-                    CRS_CUDA(crs::launch_gemm_topk(st, ix->codes, ix->count, (int)ix->row_bytes, fa.bf16 ? 1 : 0, ix->qcodes.p,
-                                                   nq, k, tau_bits, ix->cand.p, ix->num_sms, ix->gemm_cluster, &n_slices));
-                    ++launches;
-                    fa.n_lists = n_slices;
-                    fa.list_len = crs::gemm_list_len(k);
-                    ix->stats.path = 1; ix->stats.grid = n_slices * ((nq + 127) / 128); ix->stats.list_len = fa.list_len;
-                } else {
-                    for (int q = 0; q < nq; ++q) {
-                        CRS_CUDA(crs::launch_scan_f16(st, ix->codes, ix->count, ix->dim_padded, fa.bf16,
-                                                      ix->qcodes.p + (size_t)q * ix->row_bytes, tau_pre,
-                                                      ix->cand.p + (size_t)q * n_lists * M, plan));
-                        ++launches;
-                    }
-                }
-                if (ix->profiling) { CRS_CUDA(cudaEventRecord(ix->evs[ix->ev_count % 32][1], st)); ++ix->ev_count; }
-                fa.mode = 0; fa.only_flagged = 0;
-                CRS_CUDA(cudaMemsetAsync(ix->n_flagged, 0, sizeof(int32_t), st));
-                CRS_CUDA(crs::launch_finalize(st, fa));
+                    tau_pre = min_similarity - fa.eps_rel * 1.00390625f * ix->row_norm_bound;
+            }
+            if (ix->profiling) CRS_CUDA(cudaEventRecord(ix->evs[ix->ev_count % 32][0], st));
+            if (use_gemm) {
+                int n_slices = 0;
+                uint32_t tau_bits;
+                if (is_float) memcpy(&tau_bits, &tau_pre, sizeof(tau_bits)); else tau_bits = (uint32_t)min_raw;
+                const int kind = ix->store == CRS_F16 ? 0 : (ix->store == CRS_BF16 ? 1 : 2);
+                CRS_CUDA(crs::launch_gemm_topk(st, ix->codes, ix->count, (int)ix->row_bytes, kind, ix->qcodes.p, nq, k,
+                                               tau_bits, ix->cand.p, ix->num_sms, ix->gemm_cluster, &n_slices, plan.allow));
                 ++launches;
+                fa.n_lists = n_slices;
+                fa.list_len = crs::gemm_list_len(k);
+                fa.list_stride = 32;
+                ix->stats.path = 1; ix->stats.grid = n_slices * ((nq + 127) / 128); ix->stats.list_len = fa.list_len;
+            } else {
+                for (int q = 0; q < nq; ++q) {
+                    const uint8_t* qc = ix->qcodes.p + (size_t)q * ix->row_bytes;
+                    uint64_t* cd = ix->cand.p + (size_t)q * n_lists * M;
+                    if (is_float)
+                        CRS_CUDA(crs::launch_scan_f16(st, ix->codes, ix->count, ix->dim_padded, fa.bf16, qc, tau_pre, cd, plan));
+                    else if (ix->store == CRS_I8)
+                        CRS_CUDA(crs::launch_scan_i8(st, ix->codes, ix->count, ix->dim_padded, qc, min_raw, cd, plan));
+                    else
+                        CRS_CUDA(crs::launch_scan_b1(st, ix->codes, ix->count, ix->dim_padded, ix->dim, qc, min_raw, cd, plan));
+                    ++launches;
+                }
+            }
+            if (ix->profiling) { CRS_CUDA(cudaEventRecord(ix->evs[ix->ev_count % 32][1], st)); ++ix->ev_count; }
+
+            // ---- finalize: merge lists; float stores rescore + certify; integer keys are exact already and
+            // need certification only when a slice list is shorter than k
+            fa.mode = is_float ? 0 : 1;
+            fa.only_flagged = 0;
+            fa.certify_exact = (is_int && use_gemm && fa.list_len < k) ? 1 : 0;
+            certifying = is_float || fa.certify_exact;
+            if (certifying) CRS_CUDA(cudaMemsetAsync(ix->n_flagged, 0, sizeof(int32_t), st));
+            CRS_CUDA(crs::launch_finalize(st, fa));
+            ++launches;
+            if (certifying) {
                 if (out_dev) {
                     need_exact = true;          // cannot look at the flags without a sync: enqueue the conditional pass
                 } else {
@@ -511,47 +529,21 @@ static int search_impl(crs_index* ix, const void* queries, int nq, int k, float 
                     need_exact = nf > 0;
                     copied = !need_exact;
                 }
-            } else {
-                set_flags_kernel<<<(nq + 255) / 256, 256, 0, st>>>(ix->flags.p, nq, 1);
-                CRS_CUDA(cudaGetLastError());
-                ++launches;
-            }
-            if (need_exact) {
-                CRS_CUDA(crs::launch_exact_scan(st, ix->codes, ix->count, ix->dim_padded, fa.bf16, ix->qcodes.p, nq,
-                                                ix->flags.p, min_similarity, ix->cand.p, plan,
-                                                ix->force_exact ? nullptr : ix->n_flagged));
-                fa.mode = 1; fa.only_flagged = 1;
-                fa.n_lists = n_lists; fa.list_len = M;      // the exact scan writes one full list per CTA
-                CRS_CUDA(crs::launch_finalize(st, fa));
-                launches += 2;
             }
         } else {
-            const int32_t min_raw = min_raw_for(ix, min_similarity);
-            if (ix->profiling) CRS_CUDA(cudaEventRecord(ix->evs[ix->ev_count % 32][0], st));
-            if (use_gemm) {
-                // K5: exact int32 scores straight from the tensor cores; each slice list keeps >= k keys
-                int n_slices = 0;
-                CRS_CUDA(crs::launch_gemm_topk(st, ix->codes, ix->count, (int)ix->row_bytes, 2, ix->qcodes.p, nq, k,
-                                               (uint32_t)min_raw, ix->cand.p, ix->num_sms, ix->gemm_cluster, &n_slices));
-                ++launches;
-                fa.n_lists = n_slices;
-                fa.list_len = crs::gemm_list_len(k);
-                ix->stats.path = 1; ix->stats.grid = n_slices * ((nq + 127) / 128); ix->stats.list_len = fa.list_len;
-            } else {
-            for (int q = 0; q < nq; ++q) {
-                const uint8_t* qc = ix->qcodes.p + (size_t)q * ix->row_bytes;
-                uint64_t* cd = ix->cand.p + (size_t)q * n_lists * M;
-                if (ix->store == CRS_I8)
-                    CRS_CUDA(crs::launch_scan_i8(st, ix->codes, ix->count, ix->dim_padded, qc, min_raw, cd, plan));
-                else
-                    CRS_CUDA(crs::launch_scan_b1(st, ix->codes, ix->count, ix->dim_padded, ix->dim, qc, min_raw, cd, plan));
-                ++launches;
-            }
-            }
-            if (ix->profiling) { CRS_CUDA(cudaEventRecord(ix->evs[ix->ev_count % 32][1], st)); ++ix->ev_count; }
-            fa.mode = 1; fa.only_flagged = 0;
-            CRS_CUDA(crs::launch_finalize(st, fa));
+            set_flags_kernel<<<(nq + 255) / 256, 256, 0, st>>>(ix->flags.p, nq, 1);
+            CRS_CUDA(cudaGetLastError());
             ++launches;
+        }
+        if (need_exact) {
+            // exact pass over the whole shard for the flagged queries (exits at once when none is)
+            CRS_CUDA(crs::launch_exact_scan(st, ix->codes, ix->count, (int)ix->row_bytes, ix->dim, ix->store, ix->qcodes.p, nq,
+                                            ix->flags.p, min_similarity, min_raw, ix->cand.p, plan,
+                                            certifying ? ix->n_flagged : nullptr));
+            fa.mode = 1; fa.only_flagged = 1; fa.certify_exact = 0;
+            fa.n_lists = n_lists; fa.list_len = M; fa.list_stride = M;     // the exact scan writes one full list per CTA
+            CRS_CUDA(crs::launch_finalize(st, fa));
+            launches += 2;
         }
     }
 

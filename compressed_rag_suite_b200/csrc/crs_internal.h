@@ -35,11 +35,14 @@ struct FinalizeArgs {
     int n_lists;
     int list_len;              // valid entries per list (<= M = 32*lpl); a list whose last valid slot is
                                // occupied was cut there, and its cut score bounds everything it dropped
+    int list_stride;           // keys between consecutive lists of a query (>= list_len)
     int lpl;
     int nq;
     int k;
     int mode;                  // 0: float store, rescore + certify; 1: keys are already exact (ints or fallback)
     int only_flagged;          // 1: process only queries with flags[q] != 0 (fallback pass), then clear the flag
+    int certify_exact;         // mode 1 only: lists may be shorter than k -> flag queries whose k-th key does not
+                               // beat the largest list cut (integer stores on the tensor-core path)
     const void* codes;         // stored corpus rows (mode 0)
     const void* qcodes;        // [nq][dim_padded]
     const float* qnorms;       // [nq]
@@ -58,11 +61,11 @@ struct FinalizeArgs {
 };
 cudaError_t launch_finalize(cudaStream_t st, const FinalizeArgs& a);
 
-// Exact fallback for float stores: fp64-sequential score of every row for each flagged
-// query; one sorted list per CTA, keys carry the exact fl32 score.
-cudaError_t launch_exact_scan(cudaStream_t st, const void* codes, int64_t n, int dim_padded, bool bf16,
-                              const void* qcodes, int nq, const int32_t* flags, float min_similarity,
-                              uint64_t* cand, const ScanPlan& plan,
+// Exact fallback: canonical score (fp64-sequential for float stores, integer dot / Hamming
+// otherwise) of every row for each flagged query; one sorted list per CTA, keys carry the exact score.
+cudaError_t launch_exact_scan(cudaStream_t st, const void* codes, int64_t n, int row_bytes, int dim, crs_dtype store,
+                              const void* qcodes, int nq, const int32_t* flags, float min_similarity /*float stores*/,
+                              int32_t min_raw /*integer stores*/, uint64_t* cand, const ScanPlan& plan,
                               const int32_t* n_flagged /*device counter; kernel exits at once when it is 0; NULL = always run*/);
 
 // K8: canonical scores of given (query, global row id) pairs; rows of other shards -> -inf / INT32_MIN.
@@ -72,14 +75,17 @@ cudaError_t launch_score_rows(cudaStream_t st, const void* codes, int64_t n_rows
 
 // K4 / K5: tcgen05 Q*C^T with fused top-L epilogue.  kind 0 = fp16, 1 = bf16 (kind::f16, f32
 // accumulate, candidates for finalize mode 0), 2 = int8 (kind::i8, exact int32 scores, finalize
-// mode 1).  Rows of 128..768 bytes, k <= 24.  Writes one sorted list of gemm_list_len(k) keys per
-// (query, corpus slice), list stride 32; *n_slices_out = number of lists per query.
+// mode 1).  Rows of 128..768 bytes.  Writes one sorted list of gemm_list_len(k) (16 or 32) keys per
+// (query, corpus slice), list stride 32; *n_slices_out = number of lists per query.  For k above the
+// list length a slice may hold more than a list's worth of the global top-k: finalize detects that
+// (certification) and the query is recomputed by the exact fallback.
 // tau_pre_bits: threshold as float bits (kind 0/1) or int32 bits (kind 2).
 bool gemm_supported(int row_bytes, int k);
 int gemm_list_len(int k);
 cudaError_t launch_gemm_topk(cudaStream_t st, const void* codes, int64_t n, int row_bytes, int kind,
                              const void* qcodes, int nq, int k, uint32_t tau_pre_bits, uint64_t* cand, int num_sms,
-                             int cluster /*0 = auto, else 1|2|4 query tiles per multicast cluster*/, int* n_slices_out);
+                             int cluster /*0 = auto, else 1|2|4 query tiles per multicast cluster*/, int* n_slices_out,
+                             const uint32_t* allow /*optional row bitmap, applied to epilogue hits*/);
 
 // K7: merge G lists of k_in (id, raw score) per query into the global top k_out.
 cudaError_t launch_merge_topk(cudaStream_t st, const uint32_t* ids, const void* scores, int is_int,

@@ -68,13 +68,16 @@ finalize_kernel(FinalizeArgs a) {
     uint64_t e[LPL];
 #pragma unroll
     for (int s = 0; s < LPL; ++s) e[s] = 0ull;
-    const uint64_t* base = a.cand + (size_t)q * a.n_lists * M;
+    const uint64_t* base = a.cand + (size_t)q * a.n_lists * a.list_stride;
     uint64_t cut = 0ull;        // largest key at which any input list was cut (0 = no list was full)
     for (int l = warp; l < a.n_lists; l += kFinalizeWarps) {
         uint64_t b[LPL];
 #pragma unroll
-        for (int s = 0; s < LPL; ++s) b[s] = base[(size_t)l * M + lane * LPL + s];
-        cut = u64max(cut, base[(size_t)l * M + a.list_len - 1]);
+        for (int s = 0; s < LPL; ++s) {
+            const int i = lane * LPL + s;
+            b[s] = (i < a.list_len) ? base[(size_t)l * a.list_stride + i] : 0ull;
+        }
+        cut = u64max(cut, base[(size_t)l * a.list_stride + a.list_len - 1]);
         warp_merge_desc<LPL>(e, b, lane);
     }
     if (lane == 0) cut_stage[warp] = cut;
@@ -158,6 +161,31 @@ finalize_kernel(FinalizeArgs a) {
             a.flags[q] = certified ? 0 : 1;
             if (!certified) { atomicAdd(a.n_flagged, 1); atomicAdd(a.n_flagged + 1, 1); }
         }
+    } else if (a.certify_exact) {
+        // exact keys (integer stores through the tensor-core path, where each slice list keeps
+        // fewer than k keys): everything a full list dropped sorts below that list's last key,
+        // so the top-k is final iff the k-th key beats the largest such cut
+        uint64_t cutmax = 0ull;
+#pragma unroll
+        for (int w = 0; w < kFinalizeWarps; ++w) cutmax = u64max(cutmax, cut_stage[w]);
+        bool certified = true;
+        if (cutmax != 0ull) {
+            certified = false;
+            if (nvalid >= a.k) {
+                const int kk = a.k - 1;
+                uint64_t kth = 0ull;
+#pragma unroll
+                for (int s = 0; s < LPL; ++s) {
+                    const uint64_t v = shfl_u64(x[s], kk / LPL);
+                    if (s == kk % LPL) kth = v;
+                }
+                certified = kth > cutmax;
+            }
+        }
+        if (lane == 0) {
+            a.flags[q] = certified ? 0 : 1;
+            if (!certified) { atomicAdd(a.n_flagged, 1); atomicAdd(a.n_flagged + 1, 1); }
+        }
     } else if (a.only_flagged && lane == 0) {
         a.flags[q] = 0;
     }
@@ -196,11 +224,37 @@ cudaError_t launch_finalize(cudaStream_t st, const FinalizeArgs& a) {
 // flagged query, keys carry the exact fl32 score, so finalize mode 1 just merges.
 constexpr int kExactWarps = 8;
 
-template <int LPL, bool BF16>
+// canonical 32-bit orderable score of one stored row against one stored query (all stores)
+template <int STORE>
+__device__ __forceinline__ uint32_t exact_ord(const uint4* __restrict__ row, const uint4* __restrict__ q, int chunks,
+                                              int dim, float min_similarity, uint32_t ord_min, bool& pass) {
+    if constexpr (STORE == CRS_F16 || STORE == CRS_BF16) {
+        const float s = exact_dot<STORE == CRS_BF16>(row, q, chunks);
+        pass = s >= min_similarity;
+        return orderable_f32(s);
+    } else {
+        int acc = 0;
+        for (int c = 0; c < chunks; ++c) {
+            const uint4 a = row[c], b = q[c];
+            if constexpr (STORE == CRS_I8) {
+                acc = __dp4a((int)a.x, (int)b.x, acc); acc = __dp4a((int)a.y, (int)b.y, acc);
+                acc = __dp4a((int)a.z, (int)b.z, acc); acc = __dp4a((int)a.w, (int)b.w, acc);
+            } else {
+                acc += __popc(a.x ^ b.x) + __popc(a.y ^ b.y) + __popc(a.z ^ b.z) + __popc(a.w ^ b.w);
+            }
+        }
+        if constexpr (STORE == CRS_B1) acc = dim - 2 * acc;
+        const uint32_t o = orderable_i32(acc);
+        pass = o >= ord_min;
+        return o;
+    }
+}
+
+template <int LPL, int STORE>
 __global__ void __launch_bounds__(kExactWarps * 32)
-exact_scan_kernel(const uint4* __restrict__ codes, int64_t n_rows, int chunks, const uint4* __restrict__ qcodes,
-                  int nq, const int32_t* __restrict__ flags, float min_similarity, uint64_t* __restrict__ cand,
-                  const uint32_t* __restrict__ allow, const int32_t* __restrict__ n_flagged) {
+exact_scan_kernel(const uint4* __restrict__ codes, int64_t n_rows, int chunks, int dim, const uint4* __restrict__ qcodes,
+                  int nq, const int32_t* __restrict__ flags, float min_similarity, uint32_t ord_min,
+                  uint64_t* __restrict__ cand, const uint32_t* __restrict__ allow, const int32_t* __restrict__ n_flagged) {
     constexpr int M = 32 * LPL;
     // the usual case: finalize certified every query of this search -> nothing to do
     if (n_flagged != nullptr && *n_flagged == 0) return;
@@ -208,16 +262,15 @@ exact_scan_kernel(const uint4* __restrict__ codes, int64_t n_rows, int chunks, c
     __shared__ int s_list[1024];
     __shared__ int s_cnt;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // the usual case is "nothing flagged": find the flagged queries with one strided pass
-    // (4 loads per thread for 1024 queries) instead of walking nq flags serially
+    // find the flagged queries with one strided pass instead of walking nq flags serially
     for (int base = 0; base < nq; base += 1024) {
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
     for (int i = threadIdx.x; i < min(1024, nq - base); i += blockDim.x)
         if (flags[base + i] != 0) s_list[atomicAdd(&s_cnt, 1)] = base + i;
     __syncthreads();
-    const int n_flagged = s_cnt;
-    for (int j = 0; j < n_flagged; ++j) {
+    const int n_fl = s_cnt;
+    for (int j = 0; j < n_fl; ++j) {
         const int q = s_list[j];
         WarpTopM<LPL> top; top.init();
         const uint4* qv = qcodes + (size_t)q * chunks;
@@ -226,8 +279,9 @@ exact_scan_kernel(const uint4* __restrict__ codes, int64_t n_rows, int chunks, c
             const int64_t row = r0 + lane;
             uint64_t key = 0ull;
             if (row < n_rows && (allow == nullptr || ((allow[row >> 5] >> (row & 31)) & 1u))) {
-                const float s = exact_dot<BF16>(codes + row * chunks, qv, chunks);
-                if (s >= min_similarity) key = make_key(orderable_f32(s), (uint32_t)row);
+                bool pass;
+                const uint32_t o = exact_ord<STORE>(codes + row * chunks, qv, chunks, dim, min_similarity, ord_min, pass);
+                if (pass) key = make_key(o, (uint32_t)row);
             }
             unsigned bal = __ballot_sync(CRS_FULL_MASK, key > top.floor_key);
             while (bal) {
@@ -250,21 +304,35 @@ exact_scan_kernel(const uint4* __restrict__ codes, int64_t n_rows, int chunks, c
     }
 }
 
-cudaError_t launch_exact_scan(cudaStream_t st, const void* codes, int64_t n, int dim_padded, bool bf16,
-                              const void* qcodes, int nq, const int32_t* flags, float min_similarity,
+// Serial order of the flagged list (s_list is filled with atomics) does not matter: every
+// flagged query writes its own lists.
+cudaError_t launch_exact_scan(cudaStream_t st, const void* codes, int64_t n, int row_bytes, int dim, crs_dtype store,
+                              const void* qcodes, int nq, const int32_t* flags, float min_similarity, int32_t min_raw,
                               uint64_t* cand, const ScanPlan& plan, const int32_t* n_flagged) {
     if (nq <= 0) return cudaSuccess;
-    const int chunks = dim_padded / 8;
+    const int chunks = row_bytes / 16;
     const uint4* c = reinterpret_cast<const uint4*>(codes);
     const uint4* qv = reinterpret_cast<const uint4*>(qcodes);
     const int threads = kExactWarps * 32;
+    const uint32_t ord_min = orderable_i32(min_raw);
+#define CRS_EXACT(LPL_, S_) exact_scan_kernel<LPL_, S_><<<plan.grid, threads, 0, st>>>(c, n, chunks, dim, qv, nq, flags, \
+                                min_similarity, ord_min, cand, plan.allow, n_flagged)
     if (plan.lpl == 1) {
-        if (bf16) exact_scan_kernel<1, true><<<plan.grid, threads, 0, st>>>(c, n, chunks, qv, nq, flags, min_similarity, cand, plan.allow, n_flagged);
-        else      exact_scan_kernel<1, false><<<plan.grid, threads, 0, st>>>(c, n, chunks, qv, nq, flags, min_similarity, cand, plan.allow, n_flagged);
+        switch (store) {
+            case CRS_F16: CRS_EXACT(1, CRS_F16); break;
+            case CRS_BF16: CRS_EXACT(1, CRS_BF16); break;
+            case CRS_I8: CRS_EXACT(1, CRS_I8); break;
+            default: CRS_EXACT(1, CRS_B1); break;
+        }
     } else {
-        if (bf16) exact_scan_kernel<4, true><<<plan.grid, threads, 0, st>>>(c, n, chunks, qv, nq, flags, min_similarity, cand, plan.allow, n_flagged);
-        else      exact_scan_kernel<4, false><<<plan.grid, threads, 0, st>>>(c, n, chunks, qv, nq, flags, min_similarity, cand, plan.allow, n_flagged);
+        switch (store) {
+            case CRS_F16: CRS_EXACT(4, CRS_F16); break;
+            case CRS_BF16: CRS_EXACT(4, CRS_BF16); break;
+            case CRS_I8: CRS_EXACT(4, CRS_I8); break;
+            default: CRS_EXACT(4, CRS_B1); break;
+        }
     }
+#undef CRS_EXACT
     return cudaGetLastError();
 }
 

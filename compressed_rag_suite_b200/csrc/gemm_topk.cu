@@ -151,7 +151,7 @@ template <> __device__ __forceinline__ float smax<float>(float a, float b) { ret
 template <int L, bool INT>
 __device__ __forceinline__ void slab_scan(const uint32_t (&r)[32], int64_t row0, int64_t n_rows,
                                           typename ScoreT<INT>::type tau_pre, typename ScoreT<INT>::type& tau,
-                                          uint64_t (&best)[L]) {
+                                          uint64_t (&best)[L], const uint32_t* __restrict__ allow) {
     using T = typename ScoreT<INT>::type;
     T m[16];
 #pragma unroll
@@ -175,7 +175,8 @@ __device__ __forceinline__ void slab_scan(const uint32_t (&r)[32], int64_t row0,
             mask &= mask - 1;
             const T v = tmp[i];
             const int64_t row = row0 + i;
-            if (v >= tau && row < n_rows) {
+            // row bitmap of a where / where_document filter: looked up for hits only
+            if (v >= tau && row < n_rows && (allow == nullptr || ((allow[row >> 5] >> (row & 31)) & 1u))) {
                 const uint64_t key = make_key(ord_of<INT>(v), (uint32_t)row);
                 if (key > best[L - 1]) {
                     list_insert<L>(best, key);
@@ -190,7 +191,7 @@ template <int KCH, int L, int CS, bool INT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
                  int64_t n_rows, int n_qtiles, int n_slices, uint32_t idesc, uint32_t tau_pre_bits,
-                 uint64_t* __restrict__ cand, int nq, int list_stride) {
+                 uint64_t* __restrict__ cand, int nq, int list_stride, const uint32_t* __restrict__ allow) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[kStages], empty_bar[kStages], a_bar, tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_slot;
@@ -305,11 +306,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 #pragma unroll 1
             for (int slab = 0; slab < kTileC / 32; slab += 2) {
                 tmem_ld32(taddr + (slab + 1) * 32, rb);
-                slab_scan<L, INT>(ra, row0 + slab * 32, n_rows, tau_pre, tau, best);
+                slab_scan<L, INT>(ra, row0 + slab * 32, n_rows, tau_pre, tau, best, allow);
                 __syncwarp();                                       // tcgen05.ld / wait are .aligned: reconverge first
                 tmem_ld_wait();
                 if (slab + 2 < kTileC / 32) tmem_ld32(taddr + (slab + 2) * 32, ra);
-                slab_scan<L, INT>(rb, row0 + (slab + 1) * 32, n_rows, tau_pre, tau, best);
+                slab_scan<L, INT>(rb, row0 + (slab + 1) * 32, n_rows, tau_pre, tau, best, allow);
                 __syncwarp();
                 tmem_ld_wait();
             }
@@ -366,7 +367,8 @@ static bool make_map(CUtensorMap* map, const void* base, int64_t rows, int row_b
 
 template <int KCH, int L, int CS, bool INT>
 static cudaError_t launch_kch(cudaStream_t st, const CUtensorMap& mq, const CUtensorMap& mc, int64_t n, int n_qtiles,
-                              int n_slices, uint32_t idesc, uint32_t tau_pre, uint64_t* cand, int nq, int list_stride) {
+                              int n_slices, uint32_t idesc, uint32_t tau_pre, uint64_t* cand, int nq, int list_stride,
+                              const uint32_t* allow) {
     const size_t smem = (size_t)KCH * kAChunkBytes + (size_t)kStages * kBStageBytes + 1024;
     auto kern = gemm_topk_kernel<KCH, L, CS, INT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -383,28 +385,29 @@ static cudaError_t launch_kch(cudaStream_t st, const CUtensorMap& mq, const CUte
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, list_stride);
+    return cudaLaunchKernelEx(&cfg, kern, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, list_stride, allow);
 }
 
 template <int KCH, int L, bool INT>
 static cudaError_t launch_cs(int cs, cudaStream_t st, const CUtensorMap& mq, const CUtensorMap& mc, int64_t n,
-                             int n_qtiles, int n_slices, uint32_t idesc, uint32_t tau_pre, uint64_t* cand, int nq) {
-    if (cs == 4) return launch_kch<KCH, L, 4, INT>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32);
-    if (cs == 2) return launch_kch<KCH, L, 2, INT>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32);
-    return launch_kch<KCH, L, 1, INT>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32);
+                             int n_qtiles, int n_slices, uint32_t idesc, uint32_t tau_pre, uint64_t* cand, int nq,
+                             const uint32_t* allow) {
+    if (cs == 4) return launch_kch<KCH, L, 4, INT>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32, allow);
+    if (cs == 2) return launch_kch<KCH, L, 2, INT>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32, allow);
+    return launch_kch<KCH, L, 1, INT>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32, allow);
 }
 
 // kind: 0 fp16, 1 bf16, 2 int8
 bool gemm_supported(int row_bytes, int k) {
     const int kch = row_bytes / 128;
-    return (kch == 1 || kch == 2 || kch == 3 || kch == 4 || kch == 6) && k <= 24;
+    return (kch == 1 || kch == 2 || kch == 3 || kch == 4 || kch == 6) && k <= 128;
 }
 
 int gemm_list_len(int k) { return k <= 10 ? 16 : 32; }
 
 cudaError_t launch_gemm_topk(cudaStream_t st, const void* codes, int64_t n, int row_bytes, int kind,
                              const void* qcodes, int nq, int k, uint32_t tau_pre_bits, uint64_t* cand, int num_sms,
-                             int cluster, int* n_slices_out) {
+                             int cluster, int* n_slices_out, const uint32_t* allow) {
     const int kch = row_bytes / 128;
     int n_qtiles = (nq + kTileQ - 1) / kTileQ;
     // cluster size: query tiles that share one corpus stream through TMA multicast
@@ -429,10 +432,10 @@ cudaError_t launch_gemm_topk(cudaStream_t st, const void* codes, int64_t n, int 
 #define CRS_GEMM_CASE(KCH_)                                                                                              \
     case KCH_:                                                                                                           \
         if (kind == 2)                                                                                                   \
-            return L == 16 ? launch_cs<KCH_, 16, true>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq)   \
-                           : launch_cs<KCH_, 32, true>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq);  \
-        return L == 16 ? launch_cs<KCH_, 16, false>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq)      \
-                       : launch_cs<KCH_, 32, false>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq);
+            return L == 16 ? launch_cs<KCH_, 16, true>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq, allow)   \
+                           : launch_cs<KCH_, 32, true>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq, allow);  \
+        return L == 16 ? launch_cs<KCH_, 16, false>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq, allow)      \
+                       : launch_cs<KCH_, 32, false>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq, allow);
     switch (kch) {
         CRS_GEMM_CASE(1)
         CRS_GEMM_CASE(2)

@@ -327,23 +327,55 @@ def test_gemm_path_duplicates_and_fallback():
     assert ix.last_stats()["uncertified_total"] >= 1
 
 
+@pytest.mark.parametrize("store", ["f16", "bf16", "i8"])
+@pytest.mark.parametrize("n,dim,nq,k", [(40000, 384, 24, 100), (9000, 384, 16, 50), (80000, 128, 130, 100),
+                                        (2000, 256, 9, 112), (70, 384, 8, 64)])
+def test_gemm_path_large_k_bit_exact(store, n, dim, nq, k):
+    """k above the 32-key slice lists (BASELINE config 4: top-100 for a batch): certified or recomputed."""
+    x, centres = clustered(n, dim, seed=n + k)
+    q = queries_for(centres, x, nq, seed=k + 3)
+    ix = ShardIndex(dim, dtype=store)
+    ix.add(x)
+    check_search(ix, x, q, store, k)
+    assert ix.last_stats()["path"] == 1
+    check_search(ix, x, q[:9], store, k, min_similarity=0.3)
+
+
+def test_int8_gemm_large_k_overflowing_slice_takes_the_exact_fallback():
+    x, centres = clustered(40000, 384, seed=150, dup_frac=0.0)
+    x[5000:5080] = x[11]                              # 81 identical rows inside one corpus slice
+    q = np.concatenate([x[11][None], queries_for(centres, x, 15, seed=151)])
+    ix = ShardIndex(384, dtype="i8")
+    ix.add(x)
+    ids, raw, cnt = check_search(ix, x, q, "i8", 50)
+    st = ix.last_stats()
+    assert st["path"] == 1 and st["uncertified_total"] >= 1
+    assert list(ids[0]) == [11] + list(range(5000, 5049))
+    # device buffers: the conditional exact pass is enqueued without a host round trip
+    import torch
+    d = ix.search(torch.from_numpy(q).cuda(), 50)
+    assert np.array_equal(d[0].cpu().numpy().view(np.uint32), ids) and np.array_equal(d[1].cpu().numpy(), raw)
+
+
 # ---------------------------------------------------------------- N3: row-bitmap filters
 @pytest.mark.parametrize("store", ["f16", "bf16", "i8", "b1"])
 def test_filtered_search_equals_oracle_on_allowed_rows(store):
     n = 20000
     x, centres = clustered(n, 384, seed=140)
-    q = queries_for(centres, x, 12, seed=141)           # 12 queries: would take the GEMM path unfiltered
+    q = queries_for(centres, x, 12, seed=141)           # 12 queries: the tensor-core path for f16 / i8
     ix = ShardIndex(384, dtype=store)
     ix.add(x)
     rng = np.random.default_rng(142)
     codes = encode.encode_rows(x, store)
     qc = search.encode_queries(q, store)
-    for frac in (0.5, 0.01, 0.0003):
+    for frac, force in ((0.5, -1), (0.01, -1), (0.0003, -1), (0.2, 0)):
         allow = rng.random(n) < frac
         allow[17] = True
         rows = np.nonzero(allow)[0]
         want = search.search(codes[rows], qc, store, 384, 10)
+        ix.set_option("force_path", force)
         got = ix.search(q, 10, allow=allow)
+        assert ix.last_stats()["path"] == (1 if (store != "b1" and force != 0) else 0)
         assert np.array_equal(got[2], want[2])
         for i in range(len(q)):
             c = want[2][i]
