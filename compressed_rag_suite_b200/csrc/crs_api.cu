@@ -97,6 +97,7 @@ struct crs_index {
     int force_path = -1;
     int force_exact = 0;
     int gemm_cluster = 0;
+    int multi_scan = 8;         // largest group of short-row integer queries that shares one corpus pass (<= 1: off)
     int gemm_min_nq = 8;        // batches of at least this many queries take the tensor-core path
     double eps_scale = 1.0;
     // scratch
@@ -251,6 +252,7 @@ int crs_index_set_option(crs_index* ix, const char* name, int64_t value) {
     else if (!strcmp(name, "force_exact")) ix->force_exact = (int)value;
     else if (!strcmp(name, "gemm_cluster")) ix->gemm_cluster = (int)value;
     else if (!strcmp(name, "gemm_min_nq")) ix->gemm_min_nq = (int)value;
+    else if (!strcmp(name, "multi_scan")) ix->multi_scan = (int)value;
     else if (!strcmp(name, "eps_scale")) ix->eps_scale = (double)value / 1000.0;
     else if (!strcmp(name, "profiling")) {
         DeviceGuard g(ix->device);
@@ -498,6 +500,14 @@ static int search_impl(crs_index* ix, const void* queries, int nq, int k, float 
                 for (int q = 0; q < nq; ++q) {
                     const uint8_t* qc = ix->qcodes.p + (size_t)q * ix->row_bytes;
                     uint64_t* cd = ix->cand.p + (size_t)q * n_lists * M;
+                    const int grp = crs::scan_multi_group(ix->store, (int)ix->row_bytes, lpl, nq - q, ix->multi_scan);
+                    if (grp > 1) {              // a group of short-row integer queries shares one corpus pass
+                        CRS_CUDA(crs::launch_scan_int_multi(st, ix->store, ix->codes, ix->count, (int)ix->row_bytes, ix->dim,
+                                                            qc, grp, min_raw, cd, (size_t)n_lists * M, plan));
+                        q += grp - 1;
+                        ++launches;
+                        continue;
+                    }
                     if (is_float)
                         CRS_CUDA(crs::launch_scan_f16(st, ix->codes, ix->count, ix->dim_padded, fa.bf16, qc, tau_pre, cd, plan));
                     else if (ix->store == CRS_I8)

@@ -30,6 +30,13 @@ cudaError_t launch_scan_i8(cudaStream_t st, const void* codes, int64_t n, int di
 cudaError_t launch_scan_b1(cudaStream_t st, const void* codes, int64_t n, int dim_padded, int dim,
                            const void* qcodes, int32_t min_raw, uint64_t* cand, const ScanPlan& plan);
 
+// K2 / K3 for a small batch: `nq_group` (8, 4 or 2, from scan_multi_group) consecutive stored queries share
+// one pass over rows of 128 / 256 bytes; query j's lists go to cand + j * cand_q_stride.
+int scan_multi_group(crs_dtype store, int row_bytes, int lpl, int nq_left, int max_group);
+cudaError_t launch_scan_int_multi(cudaStream_t st, crs_dtype store, const void* codes, int64_t n, int row_bytes, int dim,
+                                  const void* qcodes, int nq_group, int32_t min_raw, uint64_t* cand, size_t cand_q_stride,
+                                  const ScanPlan& plan);
+
 struct FinalizeArgs {
     const uint64_t* cand;      // [nq][n_lists][M] sorted lists
     int n_lists;

@@ -342,6 +342,194 @@ scan_rows_kernel(const uint8_t* __restrict__ codes, int64_t n_rows, const uint8_
     }
 }
 
+// K2 / K3, small batches: NQ queries share ONE pass over short rows (thread per row as above).
+// A batch of b Hamming queries costs ceil(b / NQ) corpus reads instead of b (BASELINE config 5,
+// b = 8).  The queries live in shared memory in stored form; lane l reads chunk (c + l) mod CH
+// of the row AND of each query, so both loads are conflict-free LDS.128; NQ accumulators and NQ
+// warp-distributed top-M lists stay in registers.  Per row and query the result is the same
+// integer the single-query kernel computes, so the lists are identical.
+template <int KIND, int NCH, int NW, int LPL, int NQ>
+__global__ void __launch_bounds__((NW + 1) * 32, 1)
+scan_rows_multi_kernel(const uint8_t* __restrict__ codes, int64_t n_rows, const uint8_t* __restrict__ qcodes,
+                       uint32_t ord_min, int32_t b1_dim, uint64_t* __restrict__ cand, size_t cand_q_stride, int stages,
+                       const uint32_t* __restrict__ allow) {
+    static_assert(KIND == kI8 || KIND == kB1, "integer stores only");
+    constexpr int ROWB = NCH * 128;
+    constexpr int CH = NCH * 8;
+    constexpr int TILE_ROWS = NW * 32;
+    constexpr int TILE_BYTES = TILE_ROWS * ROWB;
+    constexpr int M = 32 * LPL;
+
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(16) uint8_t qs[NQ * ROWB];
+    __shared__ uint64_t full_bar[kScanMaxStages];
+    __shared__ uint64_t empty_bar[kScanMaxStages];
+    __shared__ unsigned long long cta_floor[NQ];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n_tiles = (n_rows + TILE_ROWS - 1) / TILE_ROWS;
+
+    for (int i = threadIdx.x; i < NQ * ROWB / 16; i += blockDim.x)
+        reinterpret_cast<uint4*>(qs)[i] = reinterpret_cast<const uint4*>(qcodes)[i];
+    if (threadIdx.x < NQ) cta_floor[threadIdx.x] = 0ull;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NW); }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == NW) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                const int64_t r0 = t * TILE_ROWS;
+                const uint32_t bytes = (uint32_t)(min((int64_t)TILE_ROWS, n_rows - r0) * ROWB);
+                mbar_arrive_expect_tx(&full_bar[stage], bytes);
+                bulk_g2s(smem + (size_t)stage * TILE_BYTES, codes + r0 * ROWB, bytes, &full_bar[stage]);
+                if (++stage == stages) { stage = 0; phase ^= 1; }
+            }
+        }
+        return;
+    }
+
+    WarpTopM<LPL> top[NQ];
+    uint64_t published[NQ];
+#pragma unroll
+    for (int qi = 0; qi < NQ; ++qi) { top[qi].init(); published[qi] = 0ull; }
+
+    int stage = 0; uint32_t phase = 0;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        mbar_wait(&full_bar[stage], phase);
+        const int row_in_tile = warp * 32 + lane;
+        const int64_t row = t * TILE_ROWS + row_in_tile;
+        const uint8_t* rp = smem + (size_t)stage * TILE_BYTES + (size_t)row_in_tile * ROWB;
+        int acc[NQ];
+#pragma unroll
+        for (int qi = 0; qi < NQ; ++qi) acc[qi] = 0;
+        if (row < n_rows) {
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                const int off = ((c + lane) & (CH - 1)) * 16;
+                const uint4 v = *reinterpret_cast<const uint4*>(rp + off);
+#pragma unroll
+                for (int qi = 0; qi < NQ; ++qi) {
+                    const uint4 w = *reinterpret_cast<const uint4*>(qs + qi * ROWB + off);
+                    if constexpr (KIND == kI8) {
+                        acc[qi] = __dp4a((int)v.x, (int)w.x, acc[qi]); acc[qi] = __dp4a((int)v.y, (int)w.y, acc[qi]);
+                        acc[qi] = __dp4a((int)v.z, (int)w.z, acc[qi]); acc[qi] = __dp4a((int)v.w, (int)w.w, acc[qi]);
+                    } else {
+                        acc[qi] += __popc(v.x ^ w.x) + __popc(v.y ^ w.y) + __popc(v.z ^ w.z) + __popc(v.w ^ w.w);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+
+        bool allowed = row < n_rows;
+        if (allow != nullptr && allowed) allowed = (allow[row >> 5] >> (row & 31)) & 1u;
+#pragma unroll
+        for (int qi = 0; qi < NQ; ++qi) {
+            int a = acc[qi];
+            if constexpr (KIND == kB1) a = b1_dim - 2 * a;
+            const uint32_t ord = orderable_i32(a);
+            uint64_t floor_eff = u64max(top[qi].floor_key, *reinterpret_cast<volatile unsigned long long*>(&cta_floor[qi]));
+            bool pass = allowed && (ord >= ord_min) && (ord >= key_ord(floor_eff));
+            uint64_t key = 0ull;
+            if (pass) {
+                key = make_key(ord, (uint32_t)row);
+                pass = key > floor_eff;
+            }
+            unsigned bal = __ballot_sync(CRS_FULL_MASK, pass);
+            while (bal) {
+                const int src = __ffs(bal) - 1;
+                bal &= bal - 1;
+                const uint64_t kb = shfl_u64(key, src);
+                if (kb > floor_eff) {
+                    top[qi].insert(kb, lane);
+                    floor_eff = u64max(floor_eff, top[qi].floor_key);
+                }
+            }
+            if (top[qi].floor_key > published[qi]) {
+                published[qi] = top[qi].floor_key;
+                if (lane == 0) atomicMax(&cta_floor[qi], (unsigned long long)published[qi]);
+            }
+        }
+    }
+
+    named_barrier_1<NW * 32>();                       // all copies landed, ring reusable as merge scratch
+    uint64_t* stage_keys = reinterpret_cast<uint64_t*>(smem);
+#pragma unroll
+    for (int qi = 0; qi < NQ; ++qi) {
+        warp_sort_desc<LPL>(top[qi].e, lane);
+        block_merge_lists<LPL, NW>(top[qi].e, stage_keys, warp, lane);
+        if (warp == 0) {
+#pragma unroll
+            for (int sl = 0; sl < LPL; ++sl)
+                cand[(size_t)qi * cand_q_stride + (size_t)blockIdx.x * M + lane * LPL + sl] = top[qi].e[sl];
+        }
+    }
+}
+
+template <int KIND, int NCH, int LPL, int NQ>
+static cudaError_t launch_rows_multi(cudaStream_t st, const void* codes, int64_t n, const void* qcodes, uint32_t ord_min,
+                                     int32_t b1_dim, uint64_t* cand, size_t cand_q_stride, int grid, const uint32_t* allow) {
+    // 8 top-128 lists per warp need ~200 registers per thread: half the warps for that combination
+    constexpr int NW = (NCH == 1 && !(LPL == 4 && NQ == 8)) ? 16 : 8;
+    constexpr int TILE_BYTES = NW * 32 * NCH * 128;
+    constexpr int M = 32 * LPL;
+    int stages = (190 * 1024) / TILE_BYTES;
+    if (stages > kScanMaxStages) stages = kScanMaxStages;
+    size_t smem = (size_t)stages * TILE_BYTES;
+    const size_t merge_bytes = (size_t)NW * M * sizeof(uint64_t);
+    if (smem < merge_bytes) smem = merge_bytes;
+    auto kern = scan_rows_multi_kernel<KIND, NCH, NW, LPL, NQ>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, (NW + 1) * 32, smem, st>>>(reinterpret_cast<const uint8_t*>(codes), n,
+                                            reinterpret_cast<const uint8_t*>(qcodes), ord_min, b1_dim, cand, cand_q_stride,
+                                            stages, allow);
+    return cudaGetLastError();
+}
+
+template <int KIND, int NCH, int LPL>
+static cudaError_t rows_multi_by_nq(int nq, cudaStream_t st, const void* codes, int64_t n, const void* qcodes,
+                                    uint32_t ord_min, int32_t b1_dim, uint64_t* cand, size_t cand_q_stride, int grid,
+                                    const uint32_t* allow) {
+    switch (nq) {
+        case 8: return launch_rows_multi<KIND, NCH, LPL, 8>(st, codes, n, qcodes, ord_min, b1_dim, cand, cand_q_stride, grid, allow);
+        case 4: return launch_rows_multi<KIND, NCH, LPL, 4>(st, codes, n, qcodes, ord_min, b1_dim, cand, cand_q_stride, grid, allow);
+        case 2: return launch_rows_multi<KIND, NCH, LPL, 2>(st, codes, n, qcodes, ord_min, b1_dim, cand, cand_q_stride, grid, allow);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+// Largest group of queries (8, 4, 2) the shared-pass kernel takes for this row width and list
+// size, 1 = not available (the caller scans that query alone).
+int scan_multi_group(crs_dtype store, int row_bytes, int lpl, int nq_left, int max_group) {
+    if ((store != CRS_B1 && store != CRS_I8) || (row_bytes != 128 && row_bytes != 256)) return 1;
+    int cap = (lpl == 4) ? ((row_bytes == 128) ? 8 : 4) : 8;
+    if (max_group < cap) cap = max_group;
+    for (int g = cap; g >= 2; g >>= 1) if (nq_left >= g) return g;
+    return 1;
+}
+
+cudaError_t launch_scan_int_multi(cudaStream_t st, crs_dtype store, const void* codes, int64_t n, int row_bytes, int dim,
+                                  const void* qcodes, int nq_group, int32_t min_raw, uint64_t* cand, size_t cand_q_stride,
+                                  const ScanPlan& p) {
+    const uint32_t om = orderable_i32(min_raw);
+    const int nch = row_bytes / 128;
+#define CRS_MULTI(KIND_, NCH_)                                                                                          \
+    (p.lpl == 1 ? rows_multi_by_nq<KIND_, NCH_, 1>(nq_group, st, codes, n, qcodes, om, dim, cand, cand_q_stride, p.grid, p.allow) \
+                : rows_multi_by_nq<KIND_, NCH_, 4>(nq_group, st, codes, n, qcodes, om, dim, cand, cand_q_stride, p.grid, p.allow))
+    if (store == CRS_B1) return nch == 1 ? CRS_MULTI(kB1, 1) : CRS_MULTI(kB1, 2);
+    if (store == CRS_I8) return nch == 1 ? CRS_MULTI(kI8, 1) : CRS_MULTI(kI8, 2);
+#undef CRS_MULTI
+    return cudaErrorInvalidValue;
+}
+
 template <int KIND, int NCH, int NW, int LPL>
 static cudaError_t launch_rows(cudaStream_t st, const void* codes, int64_t n, const void* qcodes, uint32_t ord_min,
                                int32_t b1_dim, uint64_t* cand, int grid, const uint32_t* allow) {

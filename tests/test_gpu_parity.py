@@ -357,6 +357,34 @@ def test_int8_gemm_large_k_overflowing_slice_takes_the_exact_fallback():
     assert np.array_equal(d[0].cpu().numpy().view(np.uint32), ids) and np.array_equal(d[1].cpu().numpy(), raw)
 
 
+# ---------------------------------------------------------------- K2/K3 shared-pass small batches
+@pytest.mark.parametrize("store,dim", [("b1", 1024), ("b1", 384), ("b1", 2048), ("i8", 128), ("i8", 200)])
+@pytest.mark.parametrize("nq,k", [(2, 10), (8, 100), (13, 100), (5, 10), (7, 32)])
+def test_shared_pass_integer_batches_bit_exact(store, dim, nq, k):
+    n = 30011
+    x, centres = clustered(n, dim, seed=dim + nq)
+    q = queries_for(centres, x, nq, seed=k)
+    ix = ShardIndex(dim, dtype=store)
+    ix.add(x)
+    ix.set_option("force_path", 0)                      # i8 batches of >= 8 would otherwise take the tensor cores
+    got = check_search(ix, x, q, store, k)
+    assert ix.last_stats()["kernel_launches"] < 1 + nq + 1, "queries must share corpus passes"
+    ix.set_option("multi_scan", 0)                      # one pass per query: same lists, same result
+    one = ix.search(q, k)
+    assert all(np.array_equal(u, v) for u, v in zip(got, one))
+    ix.set_option("multi_scan", 8)
+    thr = 0.2 if store == "i8" else 0.05
+    check_search(ix, x, q, store, k, min_similarity=thr)
+    allow = np.random.default_rng(nq).random(n) < 0.3
+    rows = np.nonzero(allow)[0]
+    want = search.search(encode.encode_rows(x, store)[rows], search.encode_queries(q, store), store, dim, k)
+    f = ix.search(q, k, allow=allow)
+    assert np.array_equal(f[2], want[2])
+    for i in range(nq):
+        c = want[2][i]
+        assert np.array_equal(f[0][i, :c], rows[want[0][i, :c].astype(np.int64)].astype(np.uint32))
+
+
 # ---------------------------------------------------------------- N3: row-bitmap filters
 @pytest.mark.parametrize("store", ["f16", "bf16", "i8", "b1"])
 def test_filtered_search_equals_oracle_on_allowed_rows(store):
