@@ -97,7 +97,8 @@ struct crs_index {
     int force_path = -1;
     int force_exact = 0;
     int gemm_cluster = 0;
-    int multi_scan = 8;         // largest group of short-row integer queries that shares one corpus pass (<= 1: off)
+    int short_lists = 1;        // integer scans with k > 32 keep 32 keys per CTA + certification (0 = full 128-key lists)
+    int multi_scan = 4;         // largest group of short-row integer queries that shares one corpus pass (<= 1: off)
     int gemm_min_nq = 8;        // batches of at least this many queries take the tensor-core path
     double eps_scale = 1.0;
     // scratch
@@ -253,6 +254,7 @@ int crs_index_set_option(crs_index* ix, const char* name, int64_t value) {
     else if (!strcmp(name, "gemm_cluster")) ix->gemm_cluster = (int)value;
     else if (!strcmp(name, "gemm_min_nq")) ix->gemm_min_nq = (int)value;
     else if (!strcmp(name, "multi_scan")) ix->multi_scan = (int)value;
+    else if (!strcmp(name, "short_lists")) ix->short_lists = (int)value;
     else if (!strcmp(name, "eps_scale")) ix->eps_scale = (double)value / 1000.0;
     else if (!strcmp(name, "profiling")) {
         DeviceGuard g(ix->device);
@@ -465,7 +467,15 @@ static int search_impl(crs_index* ix, const void* queries, int nq, int k, float 
         fa.out_ids = d_ids; fa.out_scores = d_scores; fa.out_counts = d_counts;
         fa.flags = ix->flags.p; fa.n_flagged = ix->n_flagged; fa.is_int = is_int;
 
-        ix->stats.path = 0; ix->stats.grid = plan.grid; ix->stats.list_len = M;
+        // integer scans with k > 32: every CTA keeps only its best 32 keys (the insert cost of a 128-key
+        // list is what bounds shared-pass batches) and finalize certifies that no CTA held more than 32
+        // of the global top-k; a query that fails is recomputed with full lists by the exact pass
+        const bool short_lists = is_int && !use_gemm && lpl == 4 && ix->short_lists != 0;
+        const int scan_lpl = short_lists ? 1 : lpl;
+        const int SM = 32 * scan_lpl;                       // keys per CTA list of the fast pass
+        plan.lpl = scan_lpl;
+        if (!use_gemm) { fa.list_len = SM; fa.list_stride = SM; }
+        ix->stats.path = 0; ix->stats.grid = plan.grid; ix->stats.list_len = SM;
         const int32_t min_raw = is_int ? min_raw_for(ix, min_similarity) : 0;
         bool need_exact = is_float && ix->force_exact != 0;      // test hook: skip the fast pass
         bool certifying = false;                                  // the fast pass can flag queries for the exact pass
@@ -499,11 +509,11 @@ static int search_impl(crs_index* ix, const void* queries, int nq, int k, float 
             } else {
                 for (int q = 0; q < nq; ++q) {
                     const uint8_t* qc = ix->qcodes.p + (size_t)q * ix->row_bytes;
-                    uint64_t* cd = ix->cand.p + (size_t)q * n_lists * M;
-                    const int grp = crs::scan_multi_group(ix->store, (int)ix->row_bytes, lpl, nq - q, ix->multi_scan);
+                    uint64_t* cd = ix->cand.p + (size_t)q * n_lists * SM;
+                    const int grp = crs::scan_multi_group(ix->store, (int)ix->row_bytes, scan_lpl, nq - q, ix->multi_scan);
                     if (grp > 1) {              // a group of short-row integer queries shares one corpus pass
                         CRS_CUDA(crs::launch_scan_int_multi(st, ix->store, ix->codes, ix->count, (int)ix->row_bytes, ix->dim,
-                                                            qc, grp, min_raw, cd, (size_t)n_lists * M, plan));
+                                                            qc, grp, min_raw, cd, (size_t)n_lists * SM, plan));
                         q += grp - 1;
                         ++launches;
                         continue;
@@ -523,7 +533,7 @@ static int search_impl(crs_index* ix, const void* queries, int nq, int k, float 
             // need certification only when a slice list is shorter than k
             fa.mode = is_float ? 0 : 1;
             fa.only_flagged = 0;
-            fa.certify_exact = (is_int && use_gemm && fa.list_len < k) ? 1 : 0;
+            fa.certify_exact = (is_int && fa.list_len < k) ? 1 : 0;
             certifying = is_float || fa.certify_exact;
             if (certifying) CRS_CUDA(cudaMemsetAsync(ix->n_flagged, 0, sizeof(int32_t), st));
             CRS_CUDA(crs::launch_finalize(st, fa));
@@ -547,6 +557,7 @@ static int search_impl(crs_index* ix, const void* queries, int nq, int k, float 
         }
         if (need_exact) {
             // exact pass over the whole shard for the flagged queries (exits at once when none is)
+            plan.lpl = lpl;
             CRS_CUDA(crs::launch_exact_scan(st, ix->codes, ix->count, (int)ix->row_bytes, ix->dim, ix->store, ix->qcodes.p, nq,
                                             ix->flags.p, min_similarity, min_raw, ix->cand.p, plan,
                                             certifying ? ix->n_flagged : nullptr));

@@ -408,20 +408,46 @@ scan_rows_multi_kernel(const uint8_t* __restrict__ codes, int64_t n_rows, const 
 #pragma unroll
         for (int qi = 0; qi < NQ; ++qi) acc[qi] = 0;
         if (row < n_rows) {
+            if constexpr (KIND == kI8) {
 #pragma unroll
-            for (int c = 0; c < CH; ++c) {
-                const int off = ((c + lane) & (CH - 1)) * 16;
-                const uint4 v = *reinterpret_cast<const uint4*>(rp + off);
+                for (int c = 0; c < CH; ++c) {
+                    const int off = ((c + lane) & (CH - 1)) * 16;
+                    const uint4 v = *reinterpret_cast<const uint4*>(rp + off);
 #pragma unroll
-                for (int qi = 0; qi < NQ; ++qi) {
-                    const uint4 w = *reinterpret_cast<const uint4*>(qs + qi * ROWB + off);
-                    if constexpr (KIND == kI8) {
+                    for (int qi = 0; qi < NQ; ++qi) {
+                        const uint4 w = *reinterpret_cast<const uint4*>(qs + qi * ROWB + off);
                         acc[qi] = __dp4a((int)v.x, (int)w.x, acc[qi]); acc[qi] = __dp4a((int)v.y, (int)w.y, acc[qi]);
                         acc[qi] = __dp4a((int)v.z, (int)w.z, acc[qi]); acc[qi] = __dp4a((int)v.w, (int)w.w, acc[qi]);
-                    } else {
-                        acc[qi] += __popc(v.x ^ w.x) + __popc(v.y ^ w.y) + __popc(v.z ^ w.z) + __popc(v.w ^ w.w);
                     }
                 }
+            } else {
+                // Hamming distance with a carry-save adder (first Harley-Seal level).  POPC issues at a
+                // quarter of the LOP3 rate, and the shared-pass kernel is bound by whichever pipe is busier:
+                // 4 POPC per chunk and query saturate the POPC pipe, a full two-level adder (1 POPC, 14 LOP3)
+                // saturates the ALU pipe.  Balanced point: fold the four xor words into a running `ones`
+                // bit-plane (4 LOP3) and count the two weight-2 carries (2 POPC).
+                //   h = popc(ones) + 2 * sum(popc(carries))
+                uint32_t ones[NQ];
+#pragma unroll
+                for (int qi = 0; qi < NQ; ++qi) ones[qi] = 0u;
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    const int off = ((c + lane) & (CH - 1)) * 16;
+                    const uint4 v = *reinterpret_cast<const uint4*>(rp + off);
+#pragma unroll
+                    for (int qi = 0; qi < NQ; ++qi) {
+                        const uint4 w = *reinterpret_cast<const uint4*>(qs + qi * ROWB + off);
+                        const uint32_t x0 = v.x ^ w.x, x1 = v.y ^ w.y, x2 = v.z ^ w.z, x3 = v.w ^ w.w;
+                        const uint32_t o1 = ones[qi] ^ x0 ^ x1;
+                        const uint32_t ca = (ones[qi] & x0) | (ones[qi] & x1) | (x0 & x1);
+                        const uint32_t o2 = o1 ^ x2 ^ x3;
+                        const uint32_t cb = (o1 & x2) | (o1 & x3) | (x2 & x3);
+                        ones[qi] = o2;
+                        acc[qi] += __popc(ca) + __popc(cb);
+                    }
+                }
+#pragma unroll
+                for (int qi = 0; qi < NQ; ++qi) acc[qi] = 2 * acc[qi] + __popc(ones[qi]);
             }
         }
         __syncwarp();

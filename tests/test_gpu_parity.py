@@ -385,6 +385,32 @@ def test_shared_pass_integer_batches_bit_exact(store, dim, nq, k):
         assert np.array_equal(f[0][i, :c], rows[want[0][i, :c].astype(np.int64)].astype(np.uint32))
 
 
+@pytest.mark.parametrize("store,dim", [("i8", 384), ("b1", 1024)])
+def test_integer_scan_short_lists_certify_or_fall_back(store, dim):
+    """k > 32 on the scan path: CTAs keep 32 keys; a CTA holding more of the top-k forces the exact pass."""
+    n = 50000
+    x, centres = clustered(n, dim, seed=160, dup_frac=0.0)
+    x[7000:7060] = x[3]                               # 61 identical rows in consecutive tiles of one or two CTAs
+    q = np.concatenate([x[3][None], queries_for(centres, x, 4, seed=161)])
+    ix = ShardIndex(dim, dtype=store)
+    ix.add(x)
+    ix.set_option("force_path", 0)
+    ids, raw, cnt = check_search(ix, x, q, store, 100)
+    assert ix.last_stats()["uncertified_total"] >= 1
+    assert list(ids[0][:61]) == [3] + list(range(7000, 7060))
+    before = ix.last_stats()["uncertified_total"]
+    ix.set_option("short_lists", 0)                     # full 128-key lists: same result, nothing to certify
+    full = ix.search(q, 100)
+    assert all(np.array_equal(u, v) for u, v in zip(full, (ids, raw, cnt)))
+    assert ix.last_stats()["uncertified_total"] == before
+    ix.set_option("short_lists", 1)
+    import torch
+    d = ix.search(torch.from_numpy(q).cuda(), 100, 0.1)           # device buffers + threshold
+    w = ix.search(q, 100, 0.1)
+    assert np.array_equal(d[0].cpu().numpy().view(np.uint32), w[0]) and np.array_equal(d[2].cpu().numpy(), w[2])
+    check_search(ix, x, q, store, 100, min_similarity=0.1)
+
+
 # ---------------------------------------------------------------- N3: row-bitmap filters
 @pytest.mark.parametrize("store", ["f16", "bf16", "i8", "b1"])
 def test_filtered_search_equals_oracle_on_allowed_rows(store):

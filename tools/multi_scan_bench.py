@@ -12,8 +12,9 @@ def run(n, dim, nq, k, store="b1"):
     q = torch.randn(nq, dim, device="cuda", generator=g)
     ix.set_option("profiling", 1)
     ix.set_option("force_path", 0)
-    for cap in (0, 2, 4, 8):
+    for cap, short in ((0, 0), (0, 1), (4, 0), (2, 1), (4, 1), (8, 1)):
         ix.set_option("multi_scan", cap)
+        ix.set_option("short_lists", short)
         for _ in range(3):
             ix.search(q, k)
         ks = []
@@ -21,7 +22,7 @@ def run(n, dim, nq, k, store="b1"):
             ix.search(q, k); ks.append(ix.last_kernel_ms())
         ks.sort()
         ms = ks[len(ks) // 2]
-        print(json.dumps({"store": store, "n": n, "dim": dim, "nq": nq, "k": k, "group_cap": cap, "kernel_ms": round(ms, 3),
+        print(json.dumps({"store": store, "n": n, "dim": dim, "nq": nq, "k": k, "group_cap": cap, "short_lists": short, "kernel_ms": round(ms, 3),
                           "ms_per_query": round(ms / nq, 3), "GBps_per_pass_equiv": round(n * ix.row_bytes * nq / ms / 1e6, 1),
                           "launches": ix.last_stats()["kernel_launches"]}), flush=True)
     ix.close()
@@ -29,6 +30,6 @@ def run(n, dim, nq, k, store="b1"):
 if __name__ == "__main__":
     run(32_000_000, 1024, 8, 100)
     run(32_000_000, 1024, 8, 10)
-    run(32_000_000, 1024, 4, 100)
-    run(16_000_000, 2048, 8, 100)
+    run(32_000_000, 1024, 1, 100)
+    run(12_500_000, 384, 1, 100, store="i8")
     run(16_000_000, 128, 7, 10, store="i8")
