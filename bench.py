@@ -218,7 +218,15 @@ def run_ours(a):
     sc_host = torch.empty((a.batch, a.k), dtype=torch.int32 if ix.is_int else torch.float32, pin_memory=True)
     cnt_host = torch.empty((a.batch,), dtype=torch.int32, pin_memory=True)
 
+    q_host_np = q_host.numpy()
+    out_np = (ids_host.numpy(), sc_host.numpy(), cnt_host.numpy())
+
     def step_e2e():
+        if world == 1:
+            # straight through the C ABI with HOST buffers: crs_index_search copies the queries in,
+            # runs the search, copies ids / scores / counts out and returns when they are on the host
+            ix.search(q_host_np, a.k, out=out_np)
+            return
         q_stage.copy_(q_host, non_blocking=True)                 # H2D of this step's queries
         ids, sc, cnt = searcher.search(q_stage, a.k)
         ids_host.copy_(ids, non_blocking=True)                   # D2H of this step's result
@@ -259,7 +267,8 @@ def run_ours(a):
     # launch stream and keeps the last 32 pairs, so nothing synchronises inside the timed loop
     kms = ix.kernel_ms_history()[-a.steps:]
     stats = ix.last_stats()
-    e2e_total, _ = timed(step_e2e, a.steps, 1)
+    e2e_total, _ = timed(step_e2e, a.steps, 2)
+    e2e_kms = ix.kernel_ms_history()[-a.steps:]
     # keep the same load running until nvidia-smi has sampled it a few times (the timed
     # regions above are shorter than one nvidia-smi call)
     t_probe = time.perf_counter()
@@ -325,7 +334,10 @@ def run_ours(a):
         "config": workload_config(a, world),
         "e2e": {"value": e2e_qps, "unit": UNIT,
                 "h2d_bytes_per_step": q_host.numel() * 4,
-                "d2h_bytes_per_step": ids_host.numel() * 4 + sc_host.numel() * 4 + cnt_host.numel() * 4},
+                "d2h_bytes_per_step": ids_host.numel() * 4 + sc_host.numel() * 4 + cnt_host.numel() * 4,
+                "ms_per_step": e2e_total / a.steps, "kernel_ms": sum(e2e_kms) / len(e2e_kms),
+                "call": "crs_index_search with pinned host buffers" if world == 1 else
+                        "pinned host -> device copy, sharded search (NCCL allgather + merge), device -> pinned host copy"},
         "gpu_launches": (stats["kernel_launches"] + searcher.merge_launches) * a.steps,
         "launches_per_step": stats["kernel_launches"] + searcher.merge_launches,
         "path": "tcgen05 gemm" if path == 1 else "stream scan",

@@ -18,7 +18,8 @@ struct ScanPlan {
 // K0: fp32 rows -> stored codes (normalise for cosine, cast / quantise / sign-pack).
 //   norms_out (optional, [n]): fp32 upper bound of the Euclidean norm of each STORED row.
 cudaError_t launch_encode(cudaStream_t st, const float* src, int64_t n, int dim, int dim_padded,
-                          crs_dtype store, crs_metric metric, float i8_scale, void* dst, float* norms_out);
+                          crs_dtype store, crs_metric metric, float i8_scale, void* dst, float* norms_out,
+                          int32_t* zero_word = nullptr /*optional device word the kernel sets to 0 (saves a memset node)*/);
 
 // K1: fp16 / bf16 stream scan of `n` stored rows against ONE stored query; writes one
 // sorted candidate list of M keys per CTA: cand[cta * M + i].

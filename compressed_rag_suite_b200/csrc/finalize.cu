@@ -41,13 +41,21 @@ __device__ __forceinline__ void unpack8(const uint4& v, double (&o)[8]) {
 // canonical score: sequential fp64 accumulation over j = 0..Dp-1, one rounding to fp32
 template <bool BF16>
 __device__ __forceinline__ float exact_dot(const uint4* __restrict__ row, const uint4* __restrict__ q, int chunks) {
+    // rows are multiples of 128 bytes: 8 chunks (16 loads) are issued before their 64 serial FMAs, so a
+    // row costs chunks/8 memory round trips instead of one per chunk
     double acc = 0.0;
-    for (int c = 0; c < chunks; ++c) {
-        double a[8], b[8];
-        unpack8<BF16>(row[c], a);
-        unpack8<BF16>(q[c], b);
+    for (int c0 = 0; c0 < chunks; c0 += 8) {
+        uint4 rv[8], qv[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc = fma(a[j], b[j], acc);
+        for (int i = 0; i < 8; ++i) { rv[i] = row[c0 + i]; qv[i] = q[c0 + i]; }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            double a[8], b[8];
+            unpack8<BF16>(rv[i], a);
+            unpack8<BF16>(qv[i], b);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc = fma(a[j], b[j], acc);
+        }
     }
     return (float)acc;
 }

@@ -20,8 +20,9 @@ constexpr int kIngestWarps = 4;
 template <int STORE>   // crs_dtype value
 __global__ void __launch_bounds__(kIngestWarps * 32)
 encode_kernel(const float* __restrict__ src, int64_t n, int dim, int dim_padded, int cosine,
-              double i8_mult, void* __restrict__ dst, float* __restrict__ norms_out) {
+              double i8_mult, void* __restrict__ dst, float* __restrict__ norms_out, int32_t* __restrict__ zero_word) {
     __shared__ float tile[kIngestWarps][32][33];
+    if (zero_word != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *zero_word = 0;   // per-search counter reset rides along
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row0 = ((int64_t)blockIdx.x * kIngestWarps + warp) * 32;
     if (row0 >= n) return;
@@ -36,11 +37,14 @@ encode_kernel(const float* __restrict__ src, int64_t n, int dim, int dim_padded,
         for (int r = 0; r < 32; ++r)         // 32 independent loads in flight per lane
             t[r][lane] = (r < rows_here && c < dim) ? src[(row0 + r) * dim + c] : 0.f;
         __syncwarp();
-        const int cmax = min(32, dim - c0);
-        for (int j = 0; j < cmax; ++j) {
-            const double x = (double)t[lane][j];
-            n2 = fma(x, x, n2);        // x*x is exact in fp64, so fma == mul + add
-        }
+        // columns past `dim` were staged as 0 and fma(0, 0, n2) == n2 exactly, so the tile is always
+        // walked in full: the 32 loads + converts are issued up front and only the fp64 FMA chain
+        // (the canonical sequential order j = 0..D-1) is serial
+        double xv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) xv[j] = (double)t[lane][j];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) n2 = fma(xv[j], xv[j], n2);        // x*x is exact in fp64, so fma == mul + add
         __syncwarp();
     }
     const double norm = sqrt(n2);
@@ -84,17 +88,18 @@ encode_kernel(const float* __restrict__ src, int64_t n, int dim, int dim_padded,
 }
 
 cudaError_t launch_encode(cudaStream_t st, const float* src, int64_t n, int dim, int dim_padded,
-                          crs_dtype store, crs_metric metric, float i8_scale, void* dst, float* norms_out) {
+                          crs_dtype store, crs_metric metric, float i8_scale, void* dst, float* norms_out,
+                          int32_t* zero_word) {
     if (n <= 0) return cudaSuccess;
     const int64_t rows_per_block = kIngestWarps * 32;
     const unsigned grid = (unsigned)((n + rows_per_block - 1) / rows_per_block);
     const int cosine = metric == CRS_COSINE;
     const double mult = 127.0 / (double)i8_scale;
     switch (store) {
-        case CRS_F16:  encode_kernel<CRS_F16><<<grid, kIngestWarps * 32, 0, st>>>(src, n, dim, dim_padded, cosine, mult, dst, norms_out); break;
-        case CRS_BF16: encode_kernel<CRS_BF16><<<grid, kIngestWarps * 32, 0, st>>>(src, n, dim, dim_padded, cosine, mult, dst, norms_out); break;
-        case CRS_I8:   encode_kernel<CRS_I8><<<grid, kIngestWarps * 32, 0, st>>>(src, n, dim, dim_padded, cosine, mult, dst, norms_out); break;
-        case CRS_B1:   encode_kernel<CRS_B1><<<grid, kIngestWarps * 32, 0, st>>>(src, n, dim, dim_padded, cosine, mult, dst, norms_out); break;
+        case CRS_F16:  encode_kernel<CRS_F16><<<grid, kIngestWarps * 32, 0, st>>>(src, n, dim, dim_padded, cosine, mult, dst, norms_out, zero_word); break;
+        case CRS_BF16: encode_kernel<CRS_BF16><<<grid, kIngestWarps * 32, 0, st>>>(src, n, dim, dim_padded, cosine, mult, dst, norms_out, zero_word); break;
+        case CRS_I8:   encode_kernel<CRS_I8><<<grid, kIngestWarps * 32, 0, st>>>(src, n, dim, dim_padded, cosine, mult, dst, norms_out, zero_word); break;
+        case CRS_B1:   encode_kernel<CRS_B1><<<grid, kIngestWarps * 32, 0, st>>>(src, n, dim, dim_padded, cosine, mult, dst, norms_out, zero_word); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

@@ -105,8 +105,11 @@ class ShardIndex:
         N.check(self._lib.crs_index_add(self._h, a.ctypes.data_as(C.c_void_p), a.shape[0], N.CRS_F32))
 
     # ------------------------------------------------------------------ search
-    def search(self, queries, k: int, min_similarity: float = -math.inf, allow=None):
+    def search(self, queries, k: int, min_similarity: float = -math.inf, allow=None, out=None):
         """-> (ids uint32 [nq,k], raw scores f32|i32 [nq,k], counts i32 [nq]).
+
+        out: optional preallocated host result arrays (ids, scores, counts) for the numpy form —
+        e.g. views of pinned memory, so the device->host copies of the call are asynchronous.
 
         numpy in -> numpy out (synchronous); torch CUDA in -> torch CUDA out (enqueued on
         the current stream).  ids are global row ids, padded with 0xFFFFFFFF."""
@@ -135,9 +138,16 @@ class ShardIndex:
         if q.ndim != 2 or q.shape[1] != self.dim:
             raise ValueError(f"queries must be float32 [nq, {self.dim}], got {q.shape}")
         nq = q.shape[0]
-        ids = np.empty((nq, k), dtype=np.uint32)
-        sc = np.empty((nq, k), dtype=np.int32 if self.is_int else np.float32)
-        cnt = np.empty((nq,), dtype=np.int32)
+        if out is not None:
+            ids, sc, cnt = out
+            if (ids.shape != (nq, k) or sc.shape != (nq, k) or cnt.shape != (nq,) or ids.dtype.itemsize != 4
+                    or sc.dtype.itemsize != 4 or cnt.dtype != np.int32
+                    or not (ids.flags.c_contiguous and sc.flags.c_contiguous and cnt.flags.c_contiguous)):
+                raise ValueError("out must be C-contiguous (ids [nq,k] 32-bit, scores [nq,k] 32-bit, counts [nq] int32)")
+        else:
+            ids = np.empty((nq, k), dtype=np.uint32)
+            sc = np.empty((nq, k), dtype=np.int32 if self.is_int else np.float32)
+            cnt = np.empty((nq,), dtype=np.int32)
         if allow is None:
             N.check(self._lib.crs_index_search(self._h, q.ctypes.data_as(C.c_void_p), nq, int(k), float(min_similarity),
                                                ids.ctypes.data_as(C.c_void_p), sc.ctypes.data_as(C.c_void_p),

@@ -87,7 +87,12 @@ def test_search_bit_exact(store, n, dim, k):
     ix = ShardIndex(dim, dtype=store)
     ix.add(x)
     kk = min(k, n)
+    ix.set_option("force_path", 0)                      # stream scans (K1/K2/K3)
     check_search(ix, x, q, store, kk)
+    assert ix.last_stats()["path"] == 0
+    check_search(ix, x, q[:1], store, kk)
+    ix.set_option("force_path", -1)                     # default dispatch: batches of >= 2 take the tensor cores
+    check_search(ix, x, q, store, kk)                   # where the shape allows it
 
 
 @pytest.mark.parametrize("store", ["f16", "i8", "b1"])

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from compressed_rag_suite_b200.index import ShardIndex
 
-def run(n, dim, nq, k, iters=10, store="f16", cluster=0):
+def run(n, dim, nq, k, iters=10, store="f16", cluster=0, warm=3):
     ix = ShardIndex(dim, dtype=store, reserve_rows=n)
     g = torch.Generator(device="cuda"); g.manual_seed(0)
     cen = torch.randn(4096, dim, device="cuda", generator=g); cen /= cen.norm(dim=1, keepdim=True)
@@ -18,7 +18,7 @@ def run(n, dim, nq, k, iters=10, store="f16", cluster=0):
     q = 0.6 * cen[torch.randint(0, 4096, (nq,), device="cuda", generator=g)] + 0.8 * z
     ix.set_option("profiling", 1)
     ix.set_option("gemm_cluster", cluster)
-    for _ in range(3):
+    for _ in range(warm):
         ix.search(q, k)
     torch.cuda.synchronize()
     ts, ks = [], []
@@ -36,8 +36,11 @@ def run(n, dim, nq, k, iters=10, store="f16", cluster=0):
     ix.close()
 
 if __name__ == "__main__":
-    run(10_000_000, 384, 1024, 10, cluster=2)
-    run(10_000_000, 384, 1024, 10, store="i8", cluster=2)
-    run(10_000_000, 384, 1024, 10, store="i8", cluster=1)
-    run(10_000_000, 384, 128, 10, store="i8")
-    run(10_000_000, 384, 16, 10)
+    # sustained (power-capped) numbers: 150 warm-up batches (~1 s of load) before timing
+    for cl in (2, 4, 1, 2, 4):
+        run(10_000_000, 384, 1024, 10, cluster=cl, iters=40, warm=150)
+    for cl in (2, 4):
+        run(10_000_000, 384, 1024, 10, store="i8", cluster=cl, iters=40, warm=150)
+    run(10_000_000, 384, 1024, 100, cluster=2, iters=20, warm=20)
+    run(12_500_000, 384, 16, 100, store="i8", iters=20, warm=5)
+    run(10_000_000, 384, 4, 10, iters=20, warm=5)
