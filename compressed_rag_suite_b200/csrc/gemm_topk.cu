@@ -31,6 +31,11 @@
 
 namespace crs {
 
+#ifdef CRS_GEMM_PROFILE
+// dev instrumentation: cycles the MMA issuer spends waiting for operands / for a drained accumulator
+__device__ unsigned long long g_gemm_prof[8];
+#endif
+
 constexpr int kGemmThreads = 192;
 constexpr int kTileQ = 128;        // UMMA M
 constexpr int kTileC = 256;        // UMMA N (corpus rows per tile)
@@ -94,6 +99,49 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+// ---- CTA-pair (cta_group::2) variants: one MMA spans the two SMs of a cluster; each CTA stages its own
+// 128 queries (A) and HALF of the corpus tile (B), so every SM reads half the B bytes from shared memory
+// per FLOP.  All barriers the issuing (rank-0) CTA waits on live in rank 0.
+__device__ __forceinline__ uint32_t mapa_rank0(uint32_t smem_addr) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(smem_addr));
+    return r;
+}
+// TMA load into THIS CTA's smem whose completion bytes are counted on a barrier of the pair's rank-0 CTA
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_rank0) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(bar_rank0), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_512_pair(uint32_t* smem_slot) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(smem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_512_pair(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(taddr) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_i8_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on the barrier at this offset in both CTAs of the pair once the pair-MMAs issued so far retire
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -187,18 +235,22 @@ __device__ __forceinline__ void slab_scan(const uint32_t (&r)[32], int64_t row0,
     }
 }
 
-template <int KCH, int L, int CS, bool INT>
+template <int KCH, int L, int CS, bool INT, bool PAIR>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
                  int64_t n_rows, int n_qtiles, int n_slices, uint32_t idesc, uint32_t tau_pre_bits,
                  uint64_t* __restrict__ cand, int nq, int list_stride, const uint32_t* __restrict__ allow) {
+    static_assert(!PAIR || CS == 2, "the CTA-pair MMA needs clusters of exactly two CTAs");
+    // pair mode: a stage holds this CTA's half (128 rows) of a corpus chunk -> twice the stages in the same smem
+    constexpr int STAGES = PAIR ? 2 * kStages : kStages;
+    constexpr int BSTAGE = PAIR ? kBStageBytes / 2 : kBStageBytes;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t full_bar[kStages], empty_bar[kStages], a_bar, tfull_bar[2], tempty_bar[2];
+    __shared__ uint64_t full_bar[2 * kStages], empty_bar[2 * kStages], a_bar, tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_slot;
 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;                                   // KCH x 16 KB
-    uint8_t* smem_b = smem + KCH * kAChunkBytes;              // kStages x 32 KB
+    uint8_t* smem_b = smem + KCH * kAChunkBytes;              // STAGES x BSTAGE (128 KB)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // a cluster = CS query tiles working on the same corpus slice; its CTAs split every corpus
@@ -215,12 +267,14 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     const int n_tiles = (int)(tile_hi - tile_lo);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CS); }
+        // pair mode: one commit (multicast to both CTAs) frees a stage; the accumulator-drained barrier of
+        // rank 0 collects the 4 epilogue warps of BOTH CTAs
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], PAIR ? 1 : CS); }
         mbar_init(&a_bar, 1);
-        for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], PAIR ? 8 : 4); }
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc_512(&tmem_base_slot);
+    if (warp == 1) { if constexpr (PAIR) tmem_alloc_512_pair(&tmem_base_slot); else tmem_alloc_512(&tmem_base_slot); }
     tc_fence_before();
     __syncthreads();
     if constexpr (CS > 1) cluster_sync_all();               // peers' barriers exist before anything is multicast
@@ -230,6 +284,24 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
+            if constexpr (PAIR) {
+                // both CTAs' query tiles and corpus halves are counted on rank 0's barriers
+                if (crank == 0) mbar_arrive_expect_tx(&a_bar, 2 * KCH * kAChunkBytes);
+                const uint32_t a_bar0 = mapa_rank0(smem_u32(&a_bar));
+                for (int kc = 0; kc < KCH; ++kc)
+                    tma_load_2d_pair(smem_a + kc * kAChunkBytes, &map_q, kc * (INT ? 128 : kChunkK), qtile * kTileQ, a_bar0);
+                int stage = 0; uint32_t phase = 0;
+                for (int t = 0; t < n_tiles; ++t) {
+                    const int row0 = (int)((tile_lo + t) * kTileC) + crank * (kTileC / 2);
+                    for (int kc = 0; kc < KCH; ++kc) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * BSTAGE);
+                        tma_load_2d_pair(smem_b + stage * BSTAGE, &map_c, kc * (INT ? 128 : kChunkK), row0,
+                                         mapa_rank0(smem_u32(&full_bar[stage])));
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            } else {
             mbar_arrive_expect_tx(&a_bar, KCH * kAChunkBytes);
             for (int kc = 0; kc < KCH; ++kc)
                 tma_load_2d(smem_a + kc * kAChunkBytes, &map_q, kc * (INT ? 128 : kChunkK), qtile * kTileQ, &a_bar);
@@ -249,34 +321,64 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
+            }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        // ------------------------------------------------------------ MMA issuer (pair mode: rank 0 only)
+        if (lane == 0 && (!PAIR || crank == 0)) {
             mbar_wait(&a_bar, 0);
             tc_fence_after();
+#ifdef CRS_GEMM_PROFILE
+            long long w_full = 0, w_empty = 0, t_begin = clock64();
+#endif
             int stage = 0; uint32_t phase = 0;
             for (int t = 0; t < n_tiles; ++t) {
                 const int buf = t & 1;
                 const uint32_t tphase = (t >> 1) & 1;
+#ifdef CRS_GEMM_PROFILE
+                long long c0 = clock64();
+#endif
                 mbar_wait(&tempty_bar[buf], tphase ^ 1);            // epilogue has drained this accumulator
+#ifdef CRS_GEMM_PROFILE
+                w_empty += clock64() - c0;
+#endif
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * kTileC;
                 for (int kc = 0; kc < KCH; ++kc) {
+#ifdef CRS_GEMM_PROFILE
+                    long long c1 = clock64();
+#endif
                     mbar_wait(&full_bar[stage], phase);
+#ifdef CRS_GEMM_PROFILE
+                    w_full += clock64() - c1;
+#endif
                     tc_fence_after();
                     const uint64_t a_desc = make_smem_desc(smem_u32(smem_a + kc * kAChunkBytes));
-                    const uint64_t b_desc = make_smem_desc(smem_u32(smem_b + stage * kBStageBytes));
+                    const uint64_t b_desc = make_smem_desc(smem_u32(smem_b + stage * BSTAGE));
 #pragma unroll
-                    for (int k = 0; k < kChunkK / 16; ++k)          // +32 bytes per K=16 step inside the swizzle row
-                        if constexpr (INT) umma_i8(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kc | k) != 0);
-                        else umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kc | k) != 0);
-                    if constexpr (CS == 1) umma_commit(&empty_bar[stage]);   // slot reusable once these MMAs retire
+                    for (int k = 0; k < kChunkK / 16; ++k) {        // +32 bytes per K=16 step inside the swizzle row
+                        if constexpr (PAIR) {
+                            if constexpr (INT) umma_i8_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kc | k) != 0);
+                            else umma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kc | k) != 0);
+                        } else {
+                            if constexpr (INT) umma_i8(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kc | k) != 0);
+                            else umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kc | k) != 0);
+                        }
+                    }
+                    if constexpr (PAIR) umma_commit_pair(&empty_bar[stage]);  // frees the stage in both CTAs
+                    else if constexpr (CS == 1) umma_commit(&empty_bar[stage]);   // slot reusable once these MMAs retire
                     else umma_commit_mc(&empty_bar[stage], kMask);          // ... in every CTA that writes into it
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull_bar[buf]);                       // accumulator complete
+                if constexpr (PAIR) umma_commit_pair(&tfull_bar[buf]);      // accumulators complete in both CTAs
+                else umma_commit(&tfull_bar[buf]);                          // accumulator complete
             }
+#ifdef CRS_GEMM_PROFILE
+            atomicAdd(&g_gemm_prof[0], (unsigned long long)w_full);
+            atomicAdd(&g_gemm_prof[1], (unsigned long long)w_empty);
+            atomicAdd(&g_gemm_prof[2], (unsigned long long)(clock64() - t_begin));
+            atomicAdd(&g_gemm_prof[3], 1ull);
+#endif
         }
     } else {
         // ------------------------------------------------------------ epilogue (warps 2..5)
@@ -316,7 +418,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+            if (lane == 0) {
+                if constexpr (PAIR) mbar_arrive_cluster(mapa_rank0(smem_u32(&tempty_bar[buf])));
+                else mbar_arrive(&tempty_bar[buf]);
+            }
         }
         if (q < nq) {
             uint64_t* dst = cand + ((size_t)q * n_slices + slice) * list_stride;
@@ -329,8 +434,21 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     tc_fence_before();
     __syncthreads();
     if constexpr (CS > 1) cluster_sync_all();               // no CTA leaves while peers may still signal it
-    if (warp == 1) tmem_dealloc_512(tmem_base);
+    if (warp == 1) { if constexpr (PAIR) tmem_dealloc_512_pair(tmem_base); else tmem_dealloc_512(tmem_base); }
 }
+
+#ifdef CRS_GEMM_PROFILE
+}  // namespace crs
+extern "C" __attribute__((visibility("default"))) int crs_debug_gemm_profile(unsigned long long* out8, int reset) {
+    cudaError_t e = cudaMemcpyFromSymbol(out8, crs::g_gemm_prof, sizeof(unsigned long long) * 8);
+    if (e == cudaSuccess && reset) {
+        unsigned long long z[8] = {0};
+        e = cudaMemcpyToSymbol(crs::g_gemm_prof, z, sizeof(z));
+    }
+    return e == cudaSuccess ? 0 : 2;
+}
+namespace crs {
+#endif
 
 // ---------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -365,12 +483,12 @@ static bool make_map(CUtensorMap* map, const void* base, int64_t rows, int row_b
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int KCH, int L, int CS, bool INT>
+template <int KCH, int L, int CS, bool INT, bool PAIR>
 static cudaError_t launch_kch(cudaStream_t st, const CUtensorMap& mq, const CUtensorMap& mc, int64_t n, int n_qtiles,
                               int n_slices, uint32_t idesc, uint32_t tau_pre, uint64_t* cand, int nq, int list_stride,
                               const uint32_t* allow) {
     const size_t smem = (size_t)KCH * kAChunkBytes + (size_t)kStages * kBStageBytes + 1024;
-    auto kern = gemm_topk_kernel<KCH, L, CS, INT>;
+    auto kern = gemm_topk_kernel<KCH, L, CS, INT, PAIR>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
@@ -392,9 +510,13 @@ template <int KCH, int L, bool INT>
 static cudaError_t launch_cs(int cs, cudaStream_t st, const CUtensorMap& mq, const CUtensorMap& mc, int64_t n,
                              int n_qtiles, int n_slices, uint32_t idesc, uint32_t tau_pre, uint64_t* cand, int nq,
                              const uint32_t* allow) {
-    if (cs == 4) return launch_kch<KCH, L, 4, INT>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32, allow);
-    if (cs == 2) return launch_kch<KCH, L, 2, INT>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32, allow);
-    return launch_kch<KCH, L, 1, INT>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32, allow);
+    if (cs == 22) {     // CTA pair: M = 256 across the two SMs of a cluster
+        const uint32_t idesc_pair = (idesc & ~(0x1Fu << 24)) | ((uint32_t)(2 * kTileQ >> 4) << 24);
+        return launch_kch<KCH, L, 2, INT, true>(st, mq, mc, n, n_qtiles, n_slices, idesc_pair, tau_pre, cand, nq, 32, allow);
+    }
+    if (cs == 4) return launch_kch<KCH, L, 4, INT, false>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32, allow);
+    if (cs == 2) return launch_kch<KCH, L, 2, INT, false>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32, allow);
+    return launch_kch<KCH, L, 1, INT, false>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32, allow);
 }
 
 // kind: 0 fp16, 1 bf16, 2 int8
@@ -411,7 +533,8 @@ cudaError_t launch_gemm_topk(cudaStream_t st, const void* codes, int64_t n, int 
     const int kch = row_bytes / 128;
     int n_qtiles = (nq + kTileQ - 1) / kTileQ;
     // cluster size: query tiles that share one corpus stream through TMA multicast
-    int cs = cluster > 0 ? cluster : (n_qtiles >= 2 ? 2 : 1);
+    const bool pair = (cluster == 22) && n_qtiles >= 2;      // option value 22: CTA-pair MMA (cta_group::2)
+    int cs = pair ? 2 : (cluster > 0 && cluster != 22 ? cluster : (n_qtiles >= 2 ? 2 : 1));
     if (cs != 1 && cs != 2 && cs != 4) cs = 1;
     while (cs > 1 && n_qtiles < cs) cs >>= 1;
     n_qtiles = (n_qtiles + cs - 1) / cs * cs;              // padded query tiles are all-zero (TMA OOB fill)
@@ -429,6 +552,7 @@ cudaError_t launch_gemm_topk(cudaStream_t st, const void* codes, int64_t n, int 
     const uint32_t fmt = kind == 0 ? 0u : 1u;
     const uint32_t idesc = (cfmt << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kTileC >> 3) << 17) | ((uint32_t)(kTileQ >> 4) << 24);
     const int L = gemm_list_len(k);
+    if (pair) cs = 22;
 #define CRS_GEMM_CASE(KCH_)                                                                                              \
     case KCH_:                                                                                                           \
         if (kind == 2)                                                                                                   \

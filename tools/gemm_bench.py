@@ -36,11 +36,17 @@ def run(n, dim, nq, k, iters=10, store="f16", cluster=0, warm=3):
     ix.close()
 
 if __name__ == "__main__":
+    import sys
+    if len(sys.argv) > 1 and sys.argv[1] == "burst":
+        for cl in (2, 22, 2, 22):
+            run(10_000_000, 384, 1024, 10, cluster=cl, iters=10, warm=3)
+            import time; time.sleep(3)
+        sys.exit(0)
     # sustained (power-capped) numbers: 150 warm-up batches (~1 s of load) before timing
-    for cl in (2, 4, 1, 2, 4):
+    for cl in (2, 22, 2, 22):
         run(10_000_000, 384, 1024, 10, cluster=cl, iters=40, warm=150)
-    for cl in (2, 4):
+    for cl in (2, 22):
         run(10_000_000, 384, 1024, 10, store="i8", cluster=cl, iters=40, warm=150)
-    run(10_000_000, 384, 1024, 100, cluster=2, iters=20, warm=20)
-    run(12_500_000, 384, 16, 100, store="i8", iters=20, warm=5)
-    run(10_000_000, 384, 4, 10, iters=20, warm=5)
+    run(10_000_000, 384, 1024, 100, cluster=22, iters=20, warm=20)
+    run(1_250_000, 384, 1024, 10, cluster=2, iters=20, warm=20)
+    run(1_250_000, 384, 1024, 10, cluster=22, iters=20, warm=20)

@@ -1,0 +1,41 @@
+"""Dev tool: where does the MMA issuer wait?  Needs the instrumented build (libcrs_prof.so, -DCRS_GEMM_PROFILE)."""
+import sys, os, ctypes as C
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import compressed_rag_suite_b200._native as N
+N.LIB_PATH = os.path.join(os.path.dirname(N.LIB_PATH), "libcrs_prof.so")
+import torch
+from compressed_rag_suite_b200.index import ShardIndex
+
+def run(n, dim, nq, k, store, cluster):
+    ix = ShardIndex(dim, dtype=store, reserve_rows=n)
+    g = torch.Generator(device="cuda"); g.manual_seed(0)
+    cen = torch.randn(4096, dim, device="cuda", generator=g); cen /= cen.norm(dim=1, keepdim=True)
+    for off in range(0, n, 1 << 20):
+        m = min(1 << 20, n - off)
+        z = torch.randn(m, dim, device="cuda", generator=g); z /= z.norm(dim=1, keepdim=True)
+        ix.add(0.6 * cen[torch.arange(off, off + m, device="cuda") % 4096] + 0.8 * z)
+    z = torch.randn(nq, dim, device="cuda", generator=g); z /= z.norm(dim=1, keepdim=True)
+    q = 0.6 * cen[torch.randint(0, 4096, (nq,), device="cuda", generator=g)] + 0.8 * z
+    ix.set_option("gemm_cluster", cluster)
+    ix.set_option("profiling", 1)
+    lib = N.lib()
+    buf = (C.c_ulonglong * 8)()
+    for _ in range(5):
+        ix.search(q, k)
+    torch.cuda.synchronize()
+    lib.crs_debug_gemm_profile(buf, 1)
+    for _ in range(10):
+        ix.search(q, k)
+    torch.cuda.synchronize()
+    lib.crs_debug_gemm_profile(buf, 1)
+    wf, we, tot, cnt = buf[0], buf[1], buf[2], buf[3]
+    print(f"{store} nq={nq} k={k} cluster={cluster}: kernel_ms={ix.last_kernel_ms():.3f} issuers={cnt} "
+          f"wait_operands={wf / tot:.3f} wait_accumulator_drained={we / tot:.3f} of issuer time", flush=True)
+    ix.close()
+
+if __name__ == "__main__":
+    run(10_000_000, 384, 1024, 10, "f16", 2)
+    run(10_000_000, 384, 1024, 10, "f16", 22)
+    run(10_000_000, 384, 1024, 10, "i8", 2)
+    run(10_000_000, 384, 1024, 100, "f16", 2)
+    run(10_000_000, 384, 128, 10, "f16", 0)
