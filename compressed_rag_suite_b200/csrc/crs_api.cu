@@ -98,7 +98,7 @@ struct crs_index {
     int force_exact = 0;
     int gemm_cluster = 0;
     int short_lists = 1;        // integer scans with k > 32 keep 32 keys per CTA + certification (0 = full 128-key lists)
-    int multi_scan = 4;         // largest group of short-row integer queries that shares one corpus pass (<= 1: off)
+    int multi_scan = 8;         // largest group of short-row integer queries that shares one corpus pass (<= 1: off)
     int gemm_min_nq = 2;        // batches of at least this many queries take the tensor-core path: one corpus read for
                                 // the whole batch (a 4-query batch over 10M x 384 fp16: 4.4 ms as scans, 1.1 ms here)
     double eps_scale = 1.0;

@@ -397,6 +397,10 @@ scan_rows_multi_kernel(const uint8_t* __restrict__ codes, int64_t n_rows, const 
     uint64_t published[NQ];
 #pragma unroll
     for (int qi = 0; qi < NQ; ++qi) { top[qi].init(); published[qi] = 0ull; }
+    uint32_t thr[NQ];
+#pragma unroll
+    for (int qi = 0; qi < NQ; ++qi) thr[qi] = ord_min;
+    int iter = 0;
 
     int stage = 0; uint32_t phase = 0;
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
@@ -430,6 +434,7 @@ scan_rows_multi_kernel(const uint8_t* __restrict__ codes, int64_t n_rows, const 
                 uint32_t ones[NQ];
 #pragma unroll
                 for (int qi = 0; qi < NQ; ++qi) ones[qi] = 0u;
+                const int one = (stages > 0) ? 1 : 0;              // always 1; opaque to the compiler
 #pragma unroll
                 for (int c = 0; c < CH; ++c) {
                     const int off = ((c + lane) & (CH - 1)) * 16;
@@ -443,7 +448,10 @@ scan_rows_multi_kernel(const uint8_t* __restrict__ codes, int64_t n_rows, const 
                         const uint32_t o2 = o1 ^ x2 ^ x3;
                         const uint32_t cb = (o1 & x2) | (o1 & x3) | (x2 & x3);
                         ones[qi] = o2;
-                        acc[qi] += __popc(ca) + __popc(cb);
+                        // the ALU pipe (LOP3) is the busiest one here (ncu: 75 %): the two additions are issued as
+                        // IMADs (multiplier `one` is a run-time 1) so they go to the idle FMA pipe instead
+                        acc[qi] = __popc(ca) * one + acc[qi];
+                        acc[qi] = __popc(cb) * one + acc[qi];
                     }
                 }
 #pragma unroll
@@ -454,19 +462,29 @@ scan_rows_multi_kernel(const uint8_t* __restrict__ codes, int64_t n_rows, const 
         if (lane == 0) mbar_arrive(&empty_bar[stage]);
         if (++stage == stages) { stage = 0; phase ^= 1; }
 
-        bool allowed = row < n_rows;
-        if (allow != nullptr && allowed) allowed = (allow[row >> 5] >> (row & 31)) & 1u;
+        // Common case per (row, query): ONE 32-bit compare against a cached threshold and one vote.  The
+        // threshold (largest of the caller's minimum, this warp's floor and the CTA floor, in the orderable
+        // score domain) is refreshed after every insert and every 8 tiles; a stale value is only ever too
+        // low, so nothing that belongs in the list is skipped.  Everything 64-bit happens behind the vote.
+        const bool in_range = row < n_rows;
+        const bool refresh = ((iter++) & 7) == 0;
 #pragma unroll
         for (int qi = 0; qi < NQ; ++qi) {
             int a = acc[qi];
             if constexpr (KIND == kB1) a = b1_dim - 2 * a;
             const uint32_t ord = orderable_i32(a);
+            if (refresh) {
+                const uint64_t f = u64max(top[qi].floor_key, *reinterpret_cast<volatile unsigned long long*>(&cta_floor[qi]));
+                thr[qi] = max(ord_min, key_ord(f));
+            }
+            if (!__any_sync(CRS_FULL_MASK, in_range && ord >= thr[qi])) continue;
             uint64_t floor_eff = u64max(top[qi].floor_key, *reinterpret_cast<volatile unsigned long long*>(&cta_floor[qi]));
-            bool pass = allowed && (ord >= ord_min) && (ord >= key_ord(floor_eff));
+            bool pass = in_range && (ord >= ord_min) && (ord >= key_ord(floor_eff));
             uint64_t key = 0ull;
             if (pass) {
                 key = make_key(ord, (uint32_t)row);
                 pass = key > floor_eff;
+                if (allow != nullptr && pass) pass = (allow[row >> 5] >> (row & 31)) & 1u;   // filter: hits only
             }
             unsigned bal = __ballot_sync(CRS_FULL_MASK, pass);
             while (bal) {
@@ -478,6 +496,7 @@ scan_rows_multi_kernel(const uint8_t* __restrict__ codes, int64_t n_rows, const 
                     floor_eff = u64max(floor_eff, top[qi].floor_key);
                 }
             }
+            thr[qi] = max(ord_min, key_ord(floor_eff));
             if (top[qi].floor_key > published[qi]) {
                 published[qi] = top[qi].floor_key;
                 if (lane == 0) atomicMax(&cta_floor[qi], (unsigned long long)published[qi]);

@@ -33,6 +33,12 @@ def rep_summary(path, out):
             for k in KEYS:
                 if k in d:
                     f.write(f"| {k} | {d[k][0]} | {d[k][1]} |\n")
+            # pipe mix: which execution pipe bounds a compute-bound kernel
+            for k in hdr:
+                if k not in KEYS and k.endswith(".avg.pct_of_peak_sustained_active") and (
+                        k.startswith("sm__inst_executed_pipe_") or k.startswith("smsp__issue_active")):
+                    if d[k][0] not in ("0", "", "n/a"):
+                        f.write(f"| {k} | {d[k][0]} | {d[k][1]} |\n")
             f.write("\n")
 
 
