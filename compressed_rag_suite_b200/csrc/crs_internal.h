@@ -66,6 +66,7 @@ struct FinalizeArgs {
     int32_t* flags;            // [nq] 1 = not certified (mode 0 writes, only_flagged reads)
     int32_t* n_flagged;        // device counter of uncertified queries (statistics)
     int is_int;                // raw scores are int32
+    int stage_rows;            // set by launch_finalize: candidate rows are staged in shared memory before rescoring
 };
 cudaError_t launch_finalize(cudaStream_t st, const FinalizeArgs& a);
 

@@ -20,7 +20,9 @@
 
 namespace crs {
 
-constexpr int kFinalizeWarps = 16;
+// 4 warps per query: the CTA is latency-bound (list loads, then M threads rescoring serially in fp64), so what matters
+// is how many queries are resident per SM — 128-thread CTAs fit 8+ per SM, 512-thread ones fit 2 (1024 queries: 55 -> ~15 us)
+constexpr int kFinalizeWarps = 4;
 
 template <bool BF16>
 __device__ __forceinline__ void unpack8(const uint4& v, double (&o)[8]) {
@@ -96,17 +98,35 @@ finalize_kernel(FinalizeArgs a) {
     }
     __syncthreads();
 
-    // 2. exact rescoring, one thread per candidate (float stores only)
+    // 2. exact rescoring, one thread per candidate (float stores only).  The candidate rows are scattered
+    // over HBM: when they fit, the whole CTA first copies them (and the query) into shared memory with
+    // independent coalesced loads — one memory round trip — and the serial fp64 chains then run from there
+    // (row stride + 16 bytes: the per-thread 16-byte walks of consecutive rows hit different banks).
     if (a.mode == 0) {
+        extern __shared__ __align__(16) uint8_t rows_sm[];
+        const int chunks = a.dim_padded / 8;
+        const int stride16 = chunks + 1;                       // in 16-byte units
+        const uint4* qglob = reinterpret_cast<const uint4*>(a.qcodes) + (size_t)q * chunks;
+        if (a.stage_rows) {
+            uint4* sm = reinterpret_cast<uint4*>(rows_sm);
+            for (int i = threadIdx.x; i < (M + 1) * chunks; i += blockDim.x) {
+                const int r = i / chunks, c = i - r * chunks;
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (r == M) v = qglob[c];                      // last slot: the query
+                else if (fast_keys[r] != 0ull) v = (reinterpret_cast<const uint4*>(a.codes) + (size_t)key_id(fast_keys[r]) * chunks)[c];
+                sm[(size_t)r * stride16 + c] = v;
+            }
+            __syncthreads();
+        }
         if (threadIdx.x < M) {
             const uint64_t fk = fast_keys[threadIdx.x];
             uint64_t ek = 0ull;
             float err = 0.f;
             if (fk != 0ull) {
                 const uint32_t id = key_id(fk);
-                const int chunks = a.dim_padded / 8;
-                const uint4* row = reinterpret_cast<const uint4*>(a.codes) + (size_t)id * chunks;
-                const uint4* qv = reinterpret_cast<const uint4*>(a.qcodes) + (size_t)q * chunks;
+                const uint4* row = a.stage_rows ? reinterpret_cast<const uint4*>(rows_sm) + (size_t)threadIdx.x * stride16
+                                                : reinterpret_cast<const uint4*>(a.codes) + (size_t)id * chunks;
+                const uint4* qv = a.stage_rows ? reinterpret_cast<const uint4*>(rows_sm) + (size_t)M * stride16 : qglob;
                 const float s = a.bf16 ? exact_dot<true>(row, qv, chunks) : exact_dot<false>(row, qv, chunks);
                 if (s >= a.min_similarity) ek = make_key(orderable_f32(s), id);
                 err = fabsf(unorderable_f32(key_ord(fk)) - s);
@@ -217,12 +237,28 @@ finalize_kernel(FinalizeArgs a) {
     if (lane == 0) a.out_counts[q] = count;
 }
 
-cudaError_t launch_finalize(cudaStream_t st, const FinalizeArgs& a) {
+cudaError_t launch_finalize(cudaStream_t st, const FinalizeArgs& a_in) {
+    FinalizeArgs a = a_in;
     if (a.nq <= 0) return cudaSuccess;
     if (a.k > 32 * a.lpl) return cudaErrorInvalidValue;
-    if (a.lpl == 1) finalize_kernel<1><<<a.nq, kFinalizeWarps * 32, 0, st>>>(a);
-    else if (a.lpl == 4) finalize_kernel<4><<<a.nq, kFinalizeWarps * 32, 0, st>>>(a);
-    else return cudaErrorInvalidValue;
+    // shared-memory staging of the candidate rows (mode 0): M rows + the query, padded stride
+    const int M = 32 * a.lpl;
+    const size_t row_bytes = (size_t)a.dim_padded * 2;
+    size_t smem = (a.mode == 0) ? (size_t)(M + 1) * (row_bytes + 16) : 0;
+    if (smem > 110 * 1024) smem = 0;                       // wide rows x 128 candidates: read straight from HBM
+    a.stage_rows = smem > 0 ? 1 : 0;
+    cudaError_t e = cudaSuccess;
+    if (a.lpl == 1) {
+        if (smem > 48 * 1024) e = cudaFuncSetAttribute(finalize_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        finalize_kernel<1><<<a.nq, kFinalizeWarps * 32, smem, st>>>(a);
+    } else if (a.lpl == 4) {
+        if (smem > 0) e = cudaFuncSetAttribute(finalize_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        finalize_kernel<4><<<a.nq, kFinalizeWarps * 32, smem, st>>>(a);
+    } else {
+        return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 

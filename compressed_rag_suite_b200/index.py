@@ -160,6 +160,28 @@ class ShardIndex:
                                                         cnt.ctypes.data_as(C.c_void_p)))
         return ids, sc, cnt
 
+    def capture_search(self, nq: int, k: int, min_similarity: float = -math.inf):
+        """CUDA-graph form of the device-buffer search for latency-bound callers (a single query over a
+        small shard is ~5 short kernels: their launch cost, not their run time, bounds the call).
+        Returns a GraphedSearch: copy queries into ``.queries`` ([nq, dim] float32 CUDA), call
+        ``.replay()``, read ``.ids / .scores / .counts``.  The index must not grow while the graph
+        is in use (the captured launches hold its row count and buffer addresses)."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        q = torch.zeros((nq, self.dim), dtype=torch.float32, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                      # warm-up: sizes every scratch buffer the search needs
+            for _ in range(2):
+                self.search(q, k, min_similarity)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.set_option("profiling", 0)                    # event pairs cannot be read back from a graph
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            ids, sc, cnt = self.search(q, k, min_similarity)
+        return GraphedSearch(graph, q, ids, sc, cnt, len(self))
+
     def pack_allow(self, allow) -> np.ndarray:
         """bool mask over the local rows -> uint32 bitmap (bit r%32 of word r/32)."""
         a = np.asarray(allow, dtype=bool).reshape(-1)
@@ -301,6 +323,17 @@ class ShardIndex:
         h = C.c_void_p()
         N.check(lib.crs_index_load(C.byref(h), path.encode(), int(device), int(row_base)))
         return cls(0, device=device, row_base=row_base, _handle=h)
+
+
+class GraphedSearch:
+    """One captured search (see ShardIndex.capture_search)."""
+
+    def __init__(self, graph, queries, ids, scores, counts, rows):
+        self.graph, self.queries, self.ids, self.scores, self.counts, self.rows = graph, queries, ids, scores, counts, rows
+
+    def replay(self):
+        self.graph.replay()
+        return self.ids, self.scores, self.counts
 
 
 def select_topk(ids, scores, k_out: int):

@@ -184,3 +184,20 @@ def test_two_stage_with_rematerialised_rows_equals_resident_fine_index():
     for u, v in zip(got, want):
         assert torch.equal(u.view(torch.int32) if u.dtype == torch.float32 else u,
                            v.view(torch.int32) if v.dtype == torch.float32 else v)
+
+
+def test_captured_search_graph_replays_identically():
+    x, centres = clustered(50000, 384, seed=360)
+    q = queries_for(centres, x, 6, seed=361)
+    for store, nq in (("f16", 1), ("i8", 1), ("f16", 6)):
+        ix = ShardIndex(384, dtype=store)
+        ix.add(x)
+        gs = ix.capture_search(nq, 10, 0.2)
+        for rep in range(3):
+            qq = torch.from_numpy(q[rep:rep + nq] if nq == 1 else np.roll(q, rep, axis=0)).cuda()
+            gs.queries.copy_(qq)
+            got = [t.clone() for t in gs.replay()]
+            want = ix.search(qq, 10, 0.2)
+            torch.cuda.synchronize()
+            assert all(torch.equal(u, v) for u, v in zip(got, want))
+        ix.close()

@@ -150,6 +150,16 @@ def main():
     kms = ix.kernel_ms_history()[-a.steps:]
     kernel_ms = sum(kms) / len(kms)
     stats = ix.last_stats()
+    graph_ms = None
+    if cfg == "c2" and world == 1:
+        # the same search replayed from a CUDA graph: what the GPU needs once launch cost is out of the way
+        gs = ix.capture_search(a.batch, k, thr_cos)
+        gs.queries.copy_(q)
+        graph_ms = timed_loop(torch, gs.replay, a.steps, max(a.warmup, 3), barrier)
+        ref = searcher.search(q, k, thr_cos)
+        torch.cuda.synchronize()
+        assert all(torch.equal(u, v) for u, v in zip(gs.replay(), ref)), "graph replay must return the same result"
+        ix.set_option("profiling", 1)
     t = torch.tensor([ms, kernel_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -203,6 +213,8 @@ def main():
                          "passes_per_step": passes, "peak_source": pk["source"]},
             "ingest_s": ingest_s,
         }
+        if graph_ms is not None:
+            line["cuda_graph"] = {"ms_per_step": graph_ms, "value": a.batch / (graph_ms * 1e-3), "unit": "queries/s"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
