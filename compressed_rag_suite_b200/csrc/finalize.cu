@@ -80,15 +80,27 @@ finalize_kernel(FinalizeArgs a) {
     for (int s = 0; s < LPL; ++s) e[s] = 0ull;
     const uint64_t* base = a.cand + (size_t)q * a.n_lists * a.list_stride;
     uint64_t cut = 0ull;        // largest key at which any input list was cut (0 = no list was full)
-    for (int l = warp; l < a.n_lists; l += kFinalizeWarps) {
-        uint64_t b[LPL];
+    // lists are fetched in batches of kBatch independent loads (one L2 round trip per batch, not per list)
+    constexpr int kBatch = (LPL == 1) ? 8 : 2;
+    for (int l0 = warp; l0 < a.n_lists; l0 += kFinalizeWarps * kBatch) {
+        uint64_t b[kBatch][LPL];
+        uint64_t last[kBatch];
 #pragma unroll
-        for (int s = 0; s < LPL; ++s) {
-            const int i = lane * LPL + s;
-            b[s] = (i < a.list_len) ? base[(size_t)l * a.list_stride + i] : 0ull;
+        for (int j = 0; j < kBatch; ++j) {
+            const int l = l0 + j * kFinalizeWarps;
+            const bool have = l < a.n_lists;
+#pragma unroll
+            for (int s = 0; s < LPL; ++s) {
+                const int i = lane * LPL + s;
+                b[j][s] = (have && i < a.list_len) ? base[(size_t)l * a.list_stride + i] : 0ull;
+            }
+            last[j] = have ? base[(size_t)l * a.list_stride + a.list_len - 1] : 0ull;
         }
-        cut = u64max(cut, base[(size_t)l * a.list_stride + a.list_len - 1]);
-        warp_merge_desc<LPL>(e, b, lane);
+#pragma unroll
+        for (int j = 0; j < kBatch; ++j) {
+            cut = u64max(cut, last[j]);
+            warp_merge_desc<LPL>(e, b[j], lane);
+        }
     }
     if (lane == 0) cut_stage[warp] = cut;
     block_merge_lists<LPL, kFinalizeWarps>(e, stage, warp, lane);

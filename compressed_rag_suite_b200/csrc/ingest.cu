@@ -87,6 +87,70 @@ encode_kernel(const float* __restrict__ src, int64_t n, int dim, int dim_padded,
     }
 }
 
+// K0 for a handful of rows (queries): the general kernel walks a row in 32-column steps and pays one
+// global-memory round trip per step (12 for 384 dims, twice) — 19 us for ONE query, which is what a
+// single-query search then waits for.  Here a CTA first copies its (up to) 32 rows into shared memory
+// with independent coalesced loads, and both passes run from there.  Same arithmetic, same order.
+constexpr int kSmallThreads = 128;
+
+template <int STORE>
+__global__ void __launch_bounds__(kSmallThreads)
+encode_small_kernel(const float* __restrict__ src, int64_t n, int dim, int dim_padded, int cosine,
+                    double i8_mult, void* __restrict__ dst, float* __restrict__ norms_out, int32_t* __restrict__ zero_word) {
+    extern __shared__ float rows_sm[];                       // [32][dim + 1]
+    __shared__ double s_div[32];
+    __shared__ int s_zero[32];
+    if (zero_word != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *zero_word = 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row0 = (int64_t)blockIdx.x * 32;
+    const int rows_here = (int)min((int64_t)32, n - row0);
+    const int ld = dim + 1;
+    for (int i = threadIdx.x; i < rows_here * dim; i += kSmallThreads) {
+        const int r = i / dim, c = i - r * dim;
+        rows_sm[r * ld + c] = src[(row0 + r) * dim + c];
+    }
+    __syncthreads();
+    if (warp == 0) {
+        double n2 = 0.0;
+        if (lane < rows_here) {
+            const float* t = rows_sm + lane * ld;
+            for (int j0 = 0; j0 < dim; j0 += 16) {           // loads and converts run ahead of the serial FMA chain
+                double xv[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) xv[j] = (j0 + j < dim) ? (double)t[j0 + j] : 0.0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) n2 = fma(xv[j], xv[j], n2);
+            }
+        }
+        const double norm = sqrt(n2);
+        s_div[lane] = (cosine && norm > 0.0) ? norm : 1.0;
+        s_zero[lane] = (cosine && !(norm > 0.0)) ? 1 : 0;
+        if (norms_out && lane < rows_here)
+            norms_out[row0 + lane] = cosine ? 1.00390625f : __double2float_ru(norm) * 1.00390625f;
+    }
+    __syncthreads();
+    // normalise + convert: a warp takes (row, 32 consecutive columns) so sign bits pack with one ballot
+    const int col_blocks = dim_padded / 32;
+    for (int w = warp; w < rows_here * col_blocks; w += kSmallThreads / 32) {
+        const int r = w / col_blocks, c = (w - r * col_blocks) * 32 + lane;
+        double y = 0.0;
+        if (c < dim && !s_zero[r]) y = (double)rows_sm[r * ld + c] / s_div[r];
+        const int64_t o = (row0 + r) * (int64_t)dim_padded + c;
+        if constexpr (STORE == CRS_F16) {
+            reinterpret_cast<__half*>(dst)[o] = __double2half(y);
+        } else if constexpr (STORE == CRS_BF16) {
+            reinterpret_cast<__nv_bfloat16*>(dst)[o] = __double2bfloat16(y);
+        } else if constexpr (STORE == CRS_I8) {
+            double q = rint(y * i8_mult);
+            q = fmin(127.0, fmax(-127.0, q));
+            reinterpret_cast<int8_t*>(dst)[o] = (int8_t)(int)q;
+        } else {
+            const unsigned bits = __ballot_sync(CRS_FULL_MASK, y > 0.0);
+            if (lane == 0) reinterpret_cast<uint32_t*>(dst)[o >> 5] = bits;
+        }
+    }
+}
+
 cudaError_t launch_encode(cudaStream_t st, const float* src, int64_t n, int dim, int dim_padded,
                           crs_dtype store, crs_metric metric, float i8_scale, void* dst, float* norms_out,
                           int32_t* zero_word) {
@@ -95,6 +159,25 @@ cudaError_t launch_encode(cudaStream_t st, const float* src, int64_t n, int dim,
     const unsigned grid = (unsigned)((n + rows_per_block - 1) / rows_per_block);
     const int cosine = metric == CRS_COSINE;
     const double mult = 127.0 / (double)i8_scale;
+    const size_t small_smem = (size_t)32 * (dim + 1) * sizeof(float);
+    if (n <= 4096 && small_smem <= 160 * 1024) {           // query-sized inputs
+        const unsigned g = (unsigned)((n + 31) / 32);
+#define CRS_ENC_SMALL(S)                                                                                         \
+        do {                                                                                                     \
+            cudaError_t e = cudaFuncSetAttribute(encode_small_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem); \
+            if (e != cudaSuccess) return e;                                                                      \
+            encode_small_kernel<S><<<g, kSmallThreads, small_smem, st>>>(src, n, dim, dim_padded, cosine, mult, dst, norms_out, zero_word); \
+        } while (0)
+        switch (store) {
+            case CRS_F16:  CRS_ENC_SMALL(CRS_F16); break;
+            case CRS_BF16: CRS_ENC_SMALL(CRS_BF16); break;
+            case CRS_I8:   CRS_ENC_SMALL(CRS_I8); break;
+            case CRS_B1:   CRS_ENC_SMALL(CRS_B1); break;
+            default: return cudaErrorInvalidValue;
+        }
+#undef CRS_ENC_SMALL
+        return cudaGetLastError();
+    }
     switch (store) {
         case CRS_F16:  encode_kernel<CRS_F16><<<grid, kIngestWarps * 32, 0, st>>>(src, n, dim, dim_padded, cosine, mult, dst, norms_out, zero_word); break;
         case CRS_BF16: encode_kernel<CRS_BF16><<<grid, kIngestWarps * 32, 0, st>>>(src, n, dim, dim_padded, cosine, mult, dst, norms_out, zero_word); break;

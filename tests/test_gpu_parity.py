@@ -26,9 +26,9 @@ def as_codes(raw_bytes, store, dp):
 # ---------------------------------------------------------------- K0 ingest
 @pytest.mark.parametrize("store", ["f16", "bf16", "i8", "b1"])
 @pytest.mark.parametrize("dim", [384, 100, 64, 1000])
-def test_ingest_bit_exact(store, dim):
-    rng = np.random.default_rng(dim)
-    n = 517                                        # ragged: not a multiple of the 32-row warp tile
+@pytest.mark.parametrize("n", [517, 6001])          # query-sized (shared-memory kernel) and bulk (streaming kernel) adds
+def test_ingest_bit_exact(store, dim, n):
+    rng = np.random.default_rng(dim)               # ragged n: not a multiple of the 32-row warp tile
     x = (rng.standard_normal((n, dim)) * np.exp(rng.uniform(-3, 3, (n, 1)))).astype(np.float32)
     x[7] = 0.0                                     # zero row stays zero
     x[8, :] = 0.0
