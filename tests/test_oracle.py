@@ -156,3 +156,22 @@ def test_threshold_pushdown_is_conservative():
                 assert cos >= lo
     assert postprocess.min_cosine_for_threshold(0.0) == -np.inf
     assert postprocess.min_cosine_for_threshold(1.5) == np.inf
+
+
+def test_pipelines_reduce_to_their_parts():
+    """oracle/pipelines.py: two-stage with fetch = n equals a plain fine search; MMR with zero
+    penalty keeps the relevance order; the first MMR pick is always the best hit."""
+    from oracle import pipelines
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((300, 64)).astype(np.float32)
+    q = rng.standard_normal((4, 64)).astype(np.float32)
+    ids, raw, cnt = pipelines.two_stage(x, q, 7, 300)
+    want = search.search(encode.encode_rows(x, "f16"), search.encode_queries(q, "f16"), "f16", 64, 7)
+    assert np.array_equal(ids, want[0]) and np.array_equal(raw, want[1]) and np.array_equal(cnt, want[2])
+    plain = search.search(encode.encode_rows(x, "i8"), search.encode_queries(q, "i8"), "i8", 64, 20)
+    for pen in (0.0, 0.4):
+        out = pipelines.search_then_mmr(x, q, "i8", 5, 20, pen)
+        for i, (oi, sims, rel) in enumerate(out):
+            assert oi[0] == int(plain[0][i, 0]) and len(oi) == 5 and len(set(oi)) == 5
+            if pen == 0.0:
+                assert oi == [int(v) for v in plain[0][i, :5]]

@@ -75,3 +75,67 @@ def test_pack_keeps_score_bits():
     p = pack_candidates(ids, sc)
     i2, s2 = unpack_candidates(p[None], False)
     assert torch.equal(i2[0], ids) and torch.equal(s2[0].view(torch.int32), sc.view(torch.int32))
+
+
+# ---------------------------------------------------------------- candidate-set steps over 2 ranks (configs 4 / 5)
+def _worker_stages(rank, world, port, out_dir):
+    """Host logic of the sharded MMR / two-stage pipelines on gloo: owners contribute their rows /
+    scores, everyone else the neutral element, one MAX all-reduce assembles them (the oracle stands
+    in for the local GPU calls)."""
+    from compressed_rag_suite_b200.sharded import assemble_over_shards, reference_relevance
+    from oracle import pipelines, postprocess
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n, dim, nq, fetch, k = 4000, 384, 5, 40, 10
+        x, centres = clustered(n, dim, seed=15)
+        q = queries_for(centres, x, nq, seed=16)
+        lo, hi = shard_bounds(n, world, rank)
+        # --- local top-fetch on the int8 shard, the one allgather, merge (as in the first test)
+        codes = encode.encode_rows(x, "i8")
+        qc = search.encode_queries(q, "i8")
+        ids, raw, cnt = search.search(codes[lo:hi], qc, "i8", dim, fetch, row_base=lo)
+        g = exchange_candidates(pack_candidates(torch.from_numpy(ids.view(np.int32)), torch.from_numpy(raw)))
+        g_ids, g_sc = unpack_candidates(g, True)
+        m_ids, m_raw, m_cnt = search.merge_topk(g_ids.numpy().view(np.uint32), g_sc.numpy(), fetch)
+        # --- candidate vectors: this rank fills in the rows it owns, zeros elsewhere; MAX assembles
+        vec = np.zeros((nq, fetch, dim), dtype=np.uint8)
+        own = (m_ids >= lo) & (m_ids < hi)
+        vec[own] = codes[m_ids[own].astype(np.int64)].view(np.uint8)
+        vec_t = assemble_over_shards(torch.from_numpy(vec))
+        full = codes[m_ids.astype(np.int64)].view(np.uint8)
+        assert np.array_equal(vec_t.numpy(), full), "MAX over byte codes must reproduce the owners' rows"
+        # --- fine scores: owners score, others contribute -inf; MAX assembles
+        f_codes = encode.encode_rows(x, "f16")
+        fq = search.encode_queries(q, "f16")
+        fine = np.full((nq, fetch), -np.inf, dtype=np.float32)
+        for i in range(nq):
+            sel = np.nonzero(own[i])[0]
+            fine[i, sel] = search.raw_scores(f_codes[m_ids[i, sel].astype(np.int64)], fq[i], "f16", dim)
+        fine_t = assemble_over_shards(torch.from_numpy(fine))
+        # --- relevance transform equals the reference's Python arithmetic
+        sims = search.similarity_from_raw(m_raw, "i8", dim)
+        rel = reference_relevance(torch.from_numpy(sims)).numpy()
+        want_rel = [[postprocess.distance_to_similarity(1.0 - float(s)) for s in row] for row in sims]
+        assert rel.tolist() == want_rel
+        np.savez(os.path.join(out_dir, f"stages{rank}.npz"), ids=m_ids, fine=fine_t.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_candidate_assembly(tmp_path):
+    world = 2
+    mp.spawn(_worker_stages, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    a = np.load(os.path.join(str(tmp_path), "stages0.npz"))
+    b = np.load(os.path.join(str(tmp_path), "stages1.npz"))
+    assert np.array_equal(a["ids"], b["ids"]) and np.array_equal(a["fine"], b["fine"])
+    # every candidate got its fine score from exactly one owner
+    n, dim = 4000, 384
+    x, centres = clustered(n, dim, seed=15)
+    q = queries_for(centres, x, 5, seed=16)
+    f_codes = encode.encode_rows(x, "f16")
+    fq = search.encode_queries(q, "f16")
+    for i in range(5):
+        want = search.raw_scores(f_codes[a["ids"][i].astype(np.int64)], fq[i], "f16", dim)
+        assert np.array_equal(want, a["fine"][i])
