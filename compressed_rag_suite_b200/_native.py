@@ -46,6 +46,7 @@ SYMBOLS = {
     "crs_index_score_vectors": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P]),
     "crs_select_topk": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "crs_mmr": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_double, _P]),
+    "crs_mmr_select": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_double, _P, _P, _P, _P]),
     "crs_merge_topk": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "crs_index_save": (C.c_int, [_P, C.c_char_p]),
     "crs_index_load": (C.c_int, [C.POINTER(_P), C.c_char_p, C.c_int, C.c_uint32]),

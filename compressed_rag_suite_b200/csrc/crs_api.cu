@@ -742,6 +742,26 @@ int crs_mmr(crs_index* ix, const void* vecs, const double* relevance, int nq, in
     return CRS_OK;
 }
 
+int crs_mmr_select(crs_index* ix, const void* vecs, const uint32_t* ids, const void* raw_scores, const int32_t* counts,
+                   int nq, int m, int k_out, double lambda, uint32_t* out_ids, float* out_sims, double* out_scores,
+                   int32_t* out_counts) {
+    if (!ix) return fail(CRS_EINVAL, "index is NULL");
+    if (nq < 0 || m <= 0 || k_out <= 0) return fail(CRS_EINVAL, "bad sizes");
+    if (nq == 0) return CRS_OK;
+    if (m > 128) return fail(CRS_EINVAL, "m > 128 candidates not supported");
+    const void* ptrs[] = {vecs, ids, raw_scores, counts, out_ids, out_sims, out_scores, out_counts};
+    for (const void* p : ptrs)
+        if (!is_device_ptr(p)) return fail(CRS_EINVAL, "crs_mmr_select takes device buffers");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    crs::MmrFusedArgs fa{};
+    fa.ids = ids; fa.raw = raw_scores; fa.counts = counts;
+    fa.sim_scale = (float)(((double)ix->i8_scale / 127.0) * ((double)ix->i8_scale / 127.0));
+    fa.out_ids = out_ids; fa.out_sims = out_sims; fa.out_rel = out_scores; fa.out_counts = out_counts;
+    CRS_CUDA(crs::launch_mmr(ix->stream, vecs, ix->store, ix->dim_padded, ix->dim, nullptr, nq, m, k_out, lambda, nullptr, &fa));
+    return CRS_OK;
+}
+
 int crs_merge_topk(void* cuda_stream, const uint32_t* ids, const void* scores, int is_int,
                    int n_lists, int nq, int k_in, int k_out,
                    uint32_t* out_ids, void* out_scores, int32_t* out_counts) {

@@ -101,10 +101,15 @@ cudaError_t launch_merge_topk(cudaStream_t st, const uint32_t* ids, const void* 
                               int n_lists, int nq, int k_in, int k_out,
                               uint32_t* out_ids, void* out_scores, int32_t* out_counts, bool sorted_input = true);
 
-// K6: greedy MMR over m candidate vectors per query.
+// K6: greedy MMR over m candidate vectors per query.  `fused` (optional): take the search output instead of
+// a relevance array and emit the selected hits (ids / similarity / reference score) directly.
+struct MmrFusedArgs {
+    const uint32_t* ids; const void* raw; const int32_t* counts; float sim_scale;
+    uint32_t* out_ids; float* out_sims; double* out_rel; int32_t* out_counts;
+};
 cudaError_t launch_mmr(cudaStream_t st, const void* vecs, crs_dtype store, int dim_padded, int dim,
                        const double* relevance, int nq, int m, int k_out, double lambda,
-                       int32_t* out_order);
+                       int32_t* out_order, const MmrFusedArgs* fused = nullptr);
 
 // gather stored rows by local row index
 cudaError_t launch_gather_rows(cudaStream_t st, const void* codes, size_t row_bytes, int64_t n_rows,

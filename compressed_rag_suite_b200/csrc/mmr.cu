@@ -75,10 +75,40 @@ __device__ __forceinline__ bool nep50_gt(double a, bool a32, double b, bool b32)
     return (float)a > (float)b;
 }
 
+// The reference's `score` of a hit from the raw search score, in the arithmetic Python uses
+// (rag/indexing.py:171-176 Chroma distance 1 - sim; rag/retrieval.py:75-77): every operation is an
+// explicitly rounded IEEE double op, so the compiler cannot contract them into FMAs.
+template <int STORE>
+__device__ __forceinline__ float raw_to_similarity(const void* raw, size_t i, float sim_scale, int dim) {
+    if constexpr (STORE == CRS_F16 || STORE == CRS_BF16) return reinterpret_cast<const float*>(raw)[i];
+    else if constexpr (STORE == CRS_I8) return __fmul_rn((float)reinterpret_cast<const int32_t*>(raw)[i], sim_scale);
+    else return (float)__ddiv_rn((double)reinterpret_cast<const int32_t*>(raw)[i], (double)dim);
+}
+__device__ __forceinline__ double reference_relevance(float sim) {
+    double d = __dsub_rn(1.0, (double)sim);
+    d = fmax(0.0, fmin(2.0, d));
+    const double s = __dsub_rn(1.0, __ddiv_rn(__dmul_rn(d, d), 2.0));
+    return fmax(0.0, fmin(1.0, s));
+}
+
+// Optional fused form (search -> MMR in one launch, BASELINE config 4): instead of a relevance
+// array the kernel gets the search output (ids, raw scores, counts), derives similarity and the
+// reference's relevance itself, and writes the selected ids / similarities / relevances.
+struct MmrFused {
+    const uint32_t* ids;       // [nq, m] global row ids of the candidates (nullptr = plain form)
+    const void* raw;           // [nq, m] raw scores (f32 | i32)
+    const int32_t* counts;     // [nq] valid candidates per query
+    float sim_scale;           // I8: (a/127)^2 as fp32
+    uint32_t* out_ids;         // [nq, k_out], pad 0xFFFFFFFF
+    float* out_sims;           // [nq, k_out], pad -inf
+    double* out_rel;           // [nq, k_out], pad -inf
+    int32_t* out_counts;       // [nq]
+};
+
 template <int STORE>
 __global__ void __launch_bounds__(kMmrThreads)
 mmr_kernel(const uint8_t* __restrict__ vecs, int row_bytes, int dim, const double* __restrict__ relevance,
-           int m, int k_out, double lambda, int32_t* __restrict__ out_order) {
+           int m, int k_out, double lambda, int32_t* __restrict__ out_order, MmrFused fz) {
     extern __shared__ __align__(16) uint8_t sm[];
     __shared__ double s_val[kMmrThreads];
     __shared__ uint8_t s_is32[kMmrThreads];
@@ -100,9 +130,18 @@ mmr_kernel(const uint8_t* __restrict__ vecs, int row_bytes, int dim, const doubl
     const uint8_t* mine = sm + (size_t)t * stride;
     float norm = 0.f;
     double rel = 0.0;
+    float my_sim = -INFINITY;
     if (t < m) {
         norm = __fsqrt_rn((float)mmr_dot<STORE>(mine, mine, row_bytes, dim));
-        rel = relevance[(size_t)q * m + t];
+        if (fz.ids != nullptr) {
+            rel = -INFINITY;                                   // padding candidates can never be picked
+            if (t < fz.counts[q]) {
+                my_sim = raw_to_similarity<STORE>(fz.raw, (size_t)q * m + t, fz.sim_scale, dim);
+                rel = reference_relevance(my_sim);
+            }
+        } else {
+            rel = relevance[(size_t)q * m + t];
+        }
         s_norm[t] = norm;
     }
     float max_sim = 0.f;
@@ -110,7 +149,9 @@ mmr_kernel(const uint8_t* __restrict__ vecs, int row_bytes, int dim, const doubl
     const double t1 = lambda * rel;                 // Python float product (:264)
     const float c32 = (float)(1.0 - lambda);        // (1-lambda) rounded when it meets an np.float32
 
-    if (t == 0) { s_last = 0; s_taken[0] = 1; out_order[(size_t)q * k_out] = 0; }
+    __shared__ int s_order[kMmrThreads];
+    __shared__ int s_picked;
+    if (t == 0) { s_last = 0; s_taken[0] = 1; s_order[0] = 0; s_picked = 1; }
     __syncthreads();
     const int picks = min(k_out, m);
     for (int step = 1; step < picks; ++step) {
@@ -138,19 +179,39 @@ mmr_kernel(const uint8_t* __restrict__ vecs, int row_bytes, int dim, const doubl
                 if (nep50_gt(s_val[i], s_is32[i] != 0, bv, b32)) { bv = s_val[i]; b32 = s_is32[i] != 0; best = i; }
             }
             s_last = best;
-            if (best >= 0) { s_taken[best] = 1; out_order[(size_t)q * k_out + step] = best; }
+            if (best >= 0) { s_taken[best] = 1; s_order[step] = best; s_picked = step + 1; }
         }
         __syncthreads();
-        if (s_last < 0) {            // nothing comparable left (NaNs): stop like the reference's `break`
-            if (t == 0) for (int r = step; r < k_out; ++r) out_order[(size_t)q * k_out + r] = -1;
-            return;
+        if (s_last < 0) break;       // nothing comparable left (NaNs / padding): stop like the reference's `break`
+    }
+    __syncthreads();
+    // output: the greedy order (plain form) or the selected hits themselves (fused form)
+    __shared__ float s_sim[kMmrThreads];
+    __shared__ double s_rel[kMmrThreads];
+    if (fz.ids != nullptr && t < m) { s_sim[t] = my_sim; s_rel[t] = rel; }
+    __syncthreads();
+    int picked = s_picked;
+    if (fz.ids != nullptr && fz.counts[q] == 0) picked = 0;    // position 0 is a pad too: nothing to return
+    for (int r = t; r < k_out; r += kMmrThreads) {
+        const int p = (r < picked) ? s_order[r] : -1;
+        if (out_order != nullptr) out_order[(size_t)q * k_out + r] = p;
+        if (fz.ids != nullptr) {
+            fz.out_ids[(size_t)q * k_out + r] = p >= 0 ? fz.ids[(size_t)q * m + p] : CRS_PAD_ID;
+            fz.out_sims[(size_t)q * k_out + r] = p >= 0 ? s_sim[p] : -INFINITY;
+            fz.out_rel[(size_t)q * k_out + r] = p >= 0 ? s_rel[p] : -INFINITY;
         }
     }
-    if (t == 0) for (int r = picks; r < k_out; ++r) out_order[(size_t)q * k_out + r] = -1;
+    if (fz.ids != nullptr && t == 0) fz.out_counts[q] = picked;
 }
 
 cudaError_t launch_mmr(cudaStream_t st, const void* vecs, crs_dtype store, int dim_padded, int dim,
-                       const double* relevance, int nq, int m, int k_out, double lambda, int32_t* out_order) {
+                       const double* relevance, int nq, int m, int k_out, double lambda, int32_t* out_order,
+                       const MmrFusedArgs* fused) {
+    MmrFused fz{};
+    if (fused) {
+        fz.ids = fused->ids; fz.raw = fused->raw; fz.counts = fused->counts; fz.sim_scale = fused->sim_scale;
+        fz.out_ids = fused->out_ids; fz.out_sims = fused->out_sims; fz.out_rel = fused->out_rel; fz.out_counts = fused->out_counts;
+    }
     if (nq <= 0 || m <= 0) return cudaSuccess;
     if (m > kMmrThreads || k_out <= 0) return cudaErrorInvalidValue;
     int row_bytes;
@@ -166,7 +227,7 @@ cudaError_t launch_mmr(cudaStream_t st, const void* vecs, crs_dtype store, int d
     do {                                                                                               \
         cudaError_t e = cudaFuncSetAttribute(mmr_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (e != cudaSuccess) return e;                                                                \
-        mmr_kernel<S><<<nq, kMmrThreads, smem, st>>>(v, row_bytes, dim, relevance, m, k_out, lambda, out_order);    \
+        mmr_kernel<S><<<nq, kMmrThreads, smem, st>>>(v, row_bytes, dim, relevance, m, k_out, lambda, out_order, fz);    \
     } while (0)
     switch (store) {
         case CRS_F16:  CRS_MMR_LAUNCH(CRS_F16); break;

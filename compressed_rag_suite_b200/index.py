@@ -297,6 +297,24 @@ class ShardIndex:
                                   float(lam), C.c_void_p(out.data_ptr())))
         return out
 
+    def mmr_select(self, vecs, ids, raw, counts, lam: float, k_out: int):
+        """Fused search -> MMR finish (torch CUDA tensors): candidate codes [nq, m, row_bytes], the search
+        output (ids int32 bit patterns [nq, m], raw scores [nq, m], counts [nq]) -> (ids [nq,k_out] (pad -1),
+        similarity f32 [nq,k_out], reference score f64 [nq,k_out], counts [nq]) in greedy MMR order."""
+        import torch
+        v, i, r, c = vecs.contiguous(), ids.contiguous(), raw.contiguous(), counts.contiguous()
+        nq, m = i.shape
+        dev = i.device
+        o_ids = torch.empty((nq, int(k_out)), dtype=torch.int32, device=dev)
+        o_sim = torch.empty((nq, int(k_out)), dtype=torch.float32, device=dev)
+        o_rel = torch.empty((nq, int(k_out)), dtype=torch.float64, device=dev)
+        o_cnt = torch.empty((nq,), dtype=torch.int32, device=dev)
+        self._use_torch_stream()
+        N.check(self._lib.crs_mmr_select(self._h, C.c_void_p(v.data_ptr()), C.c_void_p(i.data_ptr()), C.c_void_p(r.data_ptr()),
+                                         C.c_void_p(c.data_ptr()), nq, m, int(k_out), float(lam), C.c_void_p(o_ids.data_ptr()),
+                                         C.c_void_p(o_sim.data_ptr()), C.c_void_p(o_rel.data_ptr()), C.c_void_p(o_cnt.data_ptr())))
+        return o_ids, o_sim, o_rel, o_cnt
+
     def mmr(self, vecs: np.ndarray, relevance, lam: float, k_out: Optional[int] = None) -> np.ndarray:
         """Greedy MMR order.  vecs: [nq, m, row_bytes] uint8 stored codes (or [m, row_bytes]);
         relevance: [nq, m] float64.  -> int32 [nq, k_out] positions."""

@@ -127,16 +127,8 @@ class ShardedMMRSearcher(ShardedSearcher):
         vecs = self.index.fetch_rows_device(ids)
         if self.world > 1:
             vecs = assemble_over_shards(vecs, self.group)
-        sims = similarity_of(self.index, raw)
-        valid = torch.arange(fetch_k, device=ids.device)[None, :] < cnt[:, None]
-        rel = torch.where(valid, reference_relevance(sims), torch.full_like(sims, -math.inf, dtype=torch.float64))
-        order = self.index.mmr_device(vecs, rel, 1.0 - diversity_penalty, k)            # [nq, k], -1 = none
-        ok = order >= 0
-        pos = order.clamp(min=0).to(torch.int64)
-        out_ids = torch.where(ok, torch.gather(ids, 1, pos), torch.full_like(order, -1))
-        out_sims = torch.where(ok, torch.gather(sims, 1, pos), torch.full_like(sims[:, :k], -math.inf))
-        out_rel = torch.where(ok, torch.gather(rel, 1, pos), torch.full_like(rel[:, :k], -math.inf))
-        return out_ids, out_sims, out_rel, ok.sum(dim=1).to(torch.int32)
+        # one launch: similarity + the reference's score transform + greedy MMR + gather of the picks
+        return self.index.mmr_select(vecs, ids, raw, cnt, 1.0 - diversity_penalty, k)
 
 
 class TwoStageSearcher:

@@ -152,6 +152,17 @@ int crs_select_topk(void* cuda_stream, const uint32_t* ids, const void* scores, 
 int crs_mmr(crs_index* idx, const void* vecs, const double* relevance, int nq, int m, int k_out,
             double lambda, int32_t* out_order);
 
+/* the same selection fed straight from a search (BASELINE config 4: top-100 -> MMR -> 10, one
+ * launch): takes the candidates' stored codes plus the search output and derives, per candidate,
+ * the cosine-domain similarity and the reference's `score` (rag/retrieval.py:75-77 applied to the
+ * Chroma distance 1 - similarity, in IEEE double arithmetic as Python evaluates it); candidates
+ * at positions >= counts[q] are padding.  Device buffers only.
+ *   out_ids [nq,k_out] (pad CRS_PAD_ID), out_sims [nq,k_out] f32, out_scores [nq,k_out] f64
+ *   (the reference's `score`), out_counts [nq] */
+int crs_mmr_select(crs_index* idx, const void* vecs, const uint32_t* ids, const void* raw_scores,
+                   const int32_t* counts, int nq, int m, int k_out, double lambda,
+                   uint32_t* out_ids, float* out_sims, double* out_scores, int32_t* out_counts);
+
 /* cross-shard merge after the allgather of local top-k lists (no reference
  * counterpart: the reference is single-node).
  *   ids/scores : [n_lists, nq, k_in] device pointers;  is_int: scores are int32 */
