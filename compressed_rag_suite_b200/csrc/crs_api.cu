@@ -97,6 +97,7 @@ struct crs_index {
     int force_path = -1;
     int force_exact = 0;
     int gemm_cluster = 0;
+    int64_t sample_rows = 65536; // rows of the sample pass that seeds the contraction's per-query thresholds (0 = off)
     int short_lists = 1;        // integer scans with k > 32 keep 32 keys per CTA + certification (0 = full 128-key lists)
     int multi_scan = 8;         // largest group of short-row integer queries that shares one corpus pass (<= 1: off)
     int gemm_min_nq = 2;        // batches of at least this many queries take the tensor-core path: one corpus read for
@@ -109,7 +110,7 @@ struct crs_index {
     DevScratch<int32_t> flags, counts_dev;
     DevScratch<uint32_t> ids_dev;
     DevScratch<uint8_t> scores_dev;
-    DevScratch<uint32_t> allow_dev;
+    DevScratch<uint32_t> allow_dev, tauq;
     int32_t* n_flagged = nullptr;      // device counters: [0] uncertified this search, [1] since create,
                                        // [2] float bits of the largest |fast - exact| score seen in finalize
     crs_search_stats stats{};
@@ -234,7 +235,7 @@ int crs_index_destroy(crs_index* ix) {
         for (auto& p : ix->evs) { if (p[0]) cudaEventDestroy(p[0]); if (p[1]) cudaEventDestroy(p[1]); }
         ix->qsrc.release(); ix->qnorms.release(); ix->norms_tmp.release(); ix->qcodes.release();
         ix->stage_rows.release(); ix->vec_codes.release(); ix->cand.release(); ix->flags.release(); ix->counts_dev.release();
-        ix->ids_dev.release(); ix->scores_dev.release(); ix->allow_dev.release();
+        ix->ids_dev.release(); ix->scores_dev.release(); ix->allow_dev.release(); ix->tauq.release();
     }
     delete ix;
     return CRS_OK;
@@ -256,6 +257,7 @@ int crs_index_set_option(crs_index* ix, const char* name, int64_t value) {
     else if (!strcmp(name, "gemm_min_nq")) ix->gemm_min_nq = (int)value;
     else if (!strcmp(name, "multi_scan")) ix->multi_scan = (int)value;
     else if (!strcmp(name, "short_lists")) ix->short_lists = (int)value;
+    else if (!strcmp(name, "sample_rows")) ix->sample_rows = value;
     else if (!strcmp(name, "eps_scale")) ix->eps_scale = (double)value / 1000.0;
     else if (!strcmp(name, "profiling")) {
         DeviceGuard g(ix->device);
@@ -500,8 +502,25 @@ static int search_impl(crs_index* ix, const void* queries, int nq, int k, float 
                 uint32_t tau_bits;
                 if (is_float) memcpy(&tau_bits, &tau_pre, sizeof(tau_bits)); else tau_bits = (uint32_t)min_raw;
                 const int kind = ix->store == CRS_F16 ? 0 : (ix->store == CRS_BF16 ? 1 : 2);
+                // Sampled starting thresholds: with several query tiles the epilogue is the co-bottleneck and every
+                // (query, slice) list warms up over its first ~16K rows; a pass over the first `sample_rows` rows
+                // gives each query a floor that all slices of the full pass start from.  Valid while k fits in a
+                // slice list (the floor is the L-th best sampled key).
+                const uint32_t* tau_q = nullptr;
+                const int64_t sample = ix->sample_rows;
+                if (sample > 0 && nq > 128 && k <= crs::gemm_list_len(k) && ix->count >= 8 * sample) {
+                    int s_slices = 0;
+                    CRS_CUDA(ix->tauq.ensure((size_t)nq));
+                    CRS_CUDA(crs::launch_gemm_topk(st, ix->codes, sample, (int)ix->row_bytes, kind, ix->qcodes.p, nq, k,
+                                                   tau_bits, ix->cand.p, ix->num_sms, ix->gemm_cluster, &s_slices, plan.allow));
+                    CRS_CUDA(crs::launch_sample_tau(st, ix->cand.p, s_slices, crs::gemm_list_len(k), nq, is_int ? 1 : 0,
+                                                    ix->qnorms.p, 3.0f * fa.eps_rel * ix->row_norm_bound, ix->tauq.p));
+                    launches += 2;
+                    tau_q = ix->tauq.p;
+                    if (is_float) fa.tau_q = tau_q;
+                }
                 CRS_CUDA(crs::launch_gemm_topk(st, ix->codes, ix->count, (int)ix->row_bytes, kind, ix->qcodes.p, nq, k,
-                                               tau_bits, ix->cand.p, ix->num_sms, ix->gemm_cluster, &n_slices, plan.allow));
+                                               tau_bits, ix->cand.p, ix->num_sms, ix->gemm_cluster, &n_slices, plan.allow, tau_q));
                 ++launches;
                 fa.n_lists = n_slices;
                 fa.list_len = crs::gemm_list_len(k);

@@ -65,6 +65,7 @@ struct FinalizeArgs {
     int32_t* out_counts;       // [nq]
     int32_t* flags;            // [nq] 1 = not certified (mode 0 writes, only_flagged reads)
     int32_t* n_flagged;        // device counter of uncertified queries (statistics)
+    const uint32_t* tau_q;     // mode 0, optional: per-query fast-score floor the fast pass started from (a cut)
     int is_int;                // raw scores are int32
     int stage_rows;            // set by launch_finalize: candidate rows are staged in shared memory before rescoring
 };
@@ -94,7 +95,11 @@ int gemm_list_len(int k);
 cudaError_t launch_gemm_topk(cudaStream_t st, const void* codes, int64_t n, int row_bytes, int kind,
                              const void* qcodes, int nq, int k, uint32_t tau_pre_bits, uint64_t* cand, int num_sms,
                              int cluster /*0 = auto, else 1|2|4 query tiles per multicast cluster*/, int* n_slices_out,
-                             const uint32_t* allow /*optional row bitmap, applied to epilogue hits*/);
+                             const uint32_t* allow /*optional row bitmap, applied to epilogue hits*/,
+                             const uint32_t* tau_q = nullptr /*optional [nq] per-query starting thresholds (score bits)*/);
+// per-query starting thresholds from the lists of a sample pass (L-th best key minus margin_rel * |q|)
+cudaError_t launch_sample_tau(cudaStream_t st, const uint64_t* cand, int n_lists, int list_len, int nq, int is_int,
+                              const float* qnorms, float margin_rel, uint32_t* tau_q);
 
 // K7: merge G lists of k_in (id, raw score) per query into the global top k_out.
 cudaError_t launch_merge_topk(cudaStream_t st, const uint32_t* ids, const void* scores, int is_int,

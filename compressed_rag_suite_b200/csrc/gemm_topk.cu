@@ -239,7 +239,8 @@ template <int KCH, int L, int CS, bool INT, bool PAIR>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
                  int64_t n_rows, int n_qtiles, int n_slices, uint32_t idesc, uint32_t tau_pre_bits,
-                 uint64_t* __restrict__ cand, int nq, int list_stride, const uint32_t* __restrict__ allow) {
+                 uint64_t* __restrict__ cand, int nq, int list_stride, const uint32_t* __restrict__ allow,
+                 const uint32_t* __restrict__ tau_q) {
     static_assert(!PAIR || CS == 2, "the CTA-pair MMA needs clusters of exactly two CTAs");
     // pair mode: a stage holds this CTA's half (128 rows) of a corpus chunk -> twice the stages in the same smem
     constexpr int STAGES = PAIR ? 2 * kStages : kStages;
@@ -394,6 +395,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         const T tau_pre = score_of<INT>(tau_pre_bits);
         T tau;
         if constexpr (INT) tau = (q < nq) ? tau_pre : INT32_MAX; else tau = (q < nq) ? tau_pre : INFINITY;
+        // optional per-query starting threshold from a sample of the shard (see sample_tau_kernel): every
+        // slice starts where a scan of the sample would have ended instead of warming its list up from nothing
+        T tau_start = tau_pre;
+        if (tau_q != nullptr && q < nq) { tau_start = smax<T>(tau_pre, score_of<INT>(tau_q[q])); tau = tau_start; }
         for (int t = 0; t < n_tiles; ++t) {
             const int buf = t & 1;
             const uint32_t tphase = (t >> 1) & 1;
@@ -408,11 +413,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 #pragma unroll 1
             for (int slab = 0; slab < kTileC / 32; slab += 2) {
                 tmem_ld32(taddr + (slab + 1) * 32, rb);
-                slab_scan<L, INT>(ra, row0 + slab * 32, n_rows, tau_pre, tau, best, allow);
+                slab_scan<L, INT>(ra, row0 + slab * 32, n_rows, tau_start, tau, best, allow);
                 __syncwarp();                                       // tcgen05.ld / wait are .aligned: reconverge first
                 tmem_ld_wait();
                 if (slab + 2 < kTileC / 32) tmem_ld32(taddr + (slab + 2) * 32, ra);
-                slab_scan<L, INT>(rb, row0 + (slab + 1) * 32, n_rows, tau_pre, tau, best, allow);
+                slab_scan<L, INT>(rb, row0 + (slab + 1) * 32, n_rows, tau_start, tau, best, allow);
                 __syncwarp();
                 tmem_ld_wait();
             }
@@ -450,6 +455,44 @@ extern "C" __attribute__((visibility("default"))) int crs_debug_gemm_profile(uns
 namespace crs {
 #endif
 
+// Starting thresholds from a sample pass: the contraction above is first run over the first m rows of the
+// shard; this kernel merges each query's slice lists of that pass (one warp per query) and takes the L-th
+// best key.  There are L distinct rows scoring at least that, so with k <= L no row below it can be in the
+// top-k: it is a valid floor for EVERY slice of the full pass.  Float stores subtract `margin` (3 x the fast
+// pass' error bound) so that certification against this cut always succeeds; integer scores are exact.
+__global__ void __launch_bounds__(128)
+sample_tau_kernel(const uint64_t* __restrict__ cand, int n_lists, int list_len, int list_stride, int nq, int is_int,
+                  const float* __restrict__ qnorms, float margin_rel, uint32_t* __restrict__ tau_q) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.x * 4 + warp;
+    if (q >= nq) return;
+    uint64_t e[1] = {0ull};
+    const uint64_t* base = cand + (size_t)q * n_lists * list_stride;
+    for (int l = 0; l < n_lists; ++l) {
+        uint64_t b[1];
+        b[0] = (lane < list_len) ? base[(size_t)l * list_stride + lane] : 0ull;
+        warp_merge_desc<1>(e, b, lane);
+    }
+    const uint64_t lth = shfl_u64(e[0], list_len - 1);
+    if (lane == 0) {
+        uint32_t bits;
+        if (is_int) {
+            bits = (lth != 0ull) ? (uint32_t)unorderable_i32(key_ord(lth)) : (uint32_t)INT32_MIN;
+        } else {
+            const float t = (lth != 0ull) ? unorderable_f32(key_ord(lth)) - margin_rel * qnorms[q] : -INFINITY;
+            bits = __float_as_uint(t);
+        }
+        tau_q[q] = bits;
+    }
+}
+
+cudaError_t launch_sample_tau(cudaStream_t st, const uint64_t* cand, int n_lists, int list_len, int nq, int is_int,
+                              const float* qnorms, float margin_rel, uint32_t* tau_q) {
+    if (nq <= 0) return cudaSuccess;
+    sample_tau_kernel<<<(nq + 3) / 4, 128, 0, st>>>(cand, n_lists, list_len, 32, nq, is_int, qnorms, margin_rel, tau_q);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -486,7 +529,7 @@ static bool make_map(CUtensorMap* map, const void* base, int64_t rows, int row_b
 template <int KCH, int L, int CS, bool INT, bool PAIR>
 static cudaError_t launch_kch(cudaStream_t st, const CUtensorMap& mq, const CUtensorMap& mc, int64_t n, int n_qtiles,
                               int n_slices, uint32_t idesc, uint32_t tau_pre, uint64_t* cand, int nq, int list_stride,
-                              const uint32_t* allow) {
+                              const uint32_t* allow, const uint32_t* tau_q) {
     const size_t smem = (size_t)KCH * kAChunkBytes + (size_t)kStages * kBStageBytes + 1024;
     auto kern = gemm_topk_kernel<KCH, L, CS, INT, PAIR>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -503,20 +546,20 @@ static cudaError_t launch_kch(cudaStream_t st, const CUtensorMap& mq, const CUte
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, list_stride, allow);
+    return cudaLaunchKernelEx(&cfg, kern, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, list_stride, allow, tau_q);
 }
 
 template <int KCH, int L, bool INT>
 static cudaError_t launch_cs(int cs, cudaStream_t st, const CUtensorMap& mq, const CUtensorMap& mc, int64_t n,
                              int n_qtiles, int n_slices, uint32_t idesc, uint32_t tau_pre, uint64_t* cand, int nq,
-                             const uint32_t* allow) {
+                             const uint32_t* allow, const uint32_t* tau_q) {
     if (cs == 22) {     // CTA pair: M = 256 across the two SMs of a cluster
         const uint32_t idesc_pair = (idesc & ~(0x1Fu << 24)) | ((uint32_t)(2 * kTileQ >> 4) << 24);
-        return launch_kch<KCH, L, 2, INT, true>(st, mq, mc, n, n_qtiles, n_slices, idesc_pair, tau_pre, cand, nq, 32, allow);
+        return launch_kch<KCH, L, 2, INT, true>(st, mq, mc, n, n_qtiles, n_slices, idesc_pair, tau_pre, cand, nq, 32, allow, tau_q);
     }
-    if (cs == 4) return launch_kch<KCH, L, 4, INT, false>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32, allow);
-    if (cs == 2) return launch_kch<KCH, L, 2, INT, false>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32, allow);
-    return launch_kch<KCH, L, 1, INT, false>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32, allow);
+    if (cs == 4) return launch_kch<KCH, L, 4, INT, false>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32, allow, tau_q);
+    if (cs == 2) return launch_kch<KCH, L, 2, INT, false>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32, allow, tau_q);
+    return launch_kch<KCH, L, 1, INT, false>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32, allow, tau_q);
 }
 
 // kind: 0 fp16, 1 bf16, 2 int8
@@ -529,7 +572,7 @@ int gemm_list_len(int k) { return k <= 10 ? 16 : 32; }
 
 cudaError_t launch_gemm_topk(cudaStream_t st, const void* codes, int64_t n, int row_bytes, int kind,
                              const void* qcodes, int nq, int k, uint32_t tau_pre_bits, uint64_t* cand, int num_sms,
-                             int cluster, int* n_slices_out, const uint32_t* allow) {
+                             int cluster, int* n_slices_out, const uint32_t* allow, const uint32_t* tau_q) {
     const int kch = row_bytes / 128;
     int n_qtiles = (nq + kTileQ - 1) / kTileQ;
     // cluster size: query tiles that share one corpus stream through TMA multicast
@@ -556,10 +599,10 @@ cudaError_t launch_gemm_topk(cudaStream_t st, const void* codes, int64_t n, int 
 #define CRS_GEMM_CASE(KCH_)                                                                                              \
     case KCH_:                                                                                                           \
         if (kind == 2)                                                                                                   \
-            return L == 16 ? launch_cs<KCH_, 16, true>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq, allow)   \
-                           : launch_cs<KCH_, 32, true>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq, allow);  \
-        return L == 16 ? launch_cs<KCH_, 16, false>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq, allow)      \
-                       : launch_cs<KCH_, 32, false>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq, allow);
+            return L == 16 ? launch_cs<KCH_, 16, true>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq, allow, tau_q)   \
+                           : launch_cs<KCH_, 32, true>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq, allow, tau_q);  \
+        return L == 16 ? launch_cs<KCH_, 16, false>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq, allow, tau_q)      \
+                       : launch_cs<KCH_, 32, false>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq, allow, tau_q);
     switch (kch) {
         CRS_GEMM_CASE(1)
         CRS_GEMM_CASE(2)

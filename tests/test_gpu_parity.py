@@ -333,6 +333,37 @@ def test_gemm_path_duplicates_and_fallback():
 
 
 @pytest.mark.parametrize("store", ["f16", "bf16", "i8"])
+def test_gemm_sampled_start_thresholds_keep_results_exact(store):
+    """The contraction may start every slice from a per-query floor taken from a pass over the first rows
+    (on by default from 512K rows x > 128 queries); forced on here at a small size, with duplicates of the
+    best rows inside and outside the sample, a threshold and a filter."""
+    n, dim, nq = 24000, 384, 132
+    x, centres = clustered(n, dim, seed=170)
+    x[100:130] = x[5]                                  # 31 copies inside the sample ...
+    x[20000:20020] = x[5]                              # ... and 20 more far outside it
+    q = queries_for(centres, x, nq, seed=171)
+    q[2] = x[5]
+    ix = ShardIndex(dim, dtype=store)
+    ix.add(x)
+    ix.set_option("sample_rows", 4096)
+    for k in (10, 24):
+        got = check_search(ix, x, q, store, k)
+        assert ix.last_stats()["path"] == 1 and ix.last_stats()["kernel_launches"] >= 5
+        ix.set_option("sample_rows", 0)
+        plain = ix.search(q, k)
+        ix.set_option("sample_rows", 4096)
+        assert all(np.array_equal(u, v) for u, v in zip(got, plain))
+    assert list(got[0][2][:24]) == [5] + list(range(100, 123))
+    check_search(ix, x, q, store, 10, min_similarity=0.3)
+    allow = np.random.default_rng(3).random(n) < 0.5
+    rows = np.nonzero(allow)[0]
+    want = search.search(encode.encode_rows(x, store)[rows], search.encode_queries(q, store), store, dim, 10)
+    f = ix.search(q, 10, allow=allow)
+    assert np.array_equal(f[2], want[2])
+    assert np.array_equal(f[0], rows[want[0].astype(np.int64)].astype(np.uint32))
+
+
+@pytest.mark.parametrize("store", ["f16", "bf16", "i8"])
 @pytest.mark.parametrize("n,dim,nq,k", [(40000, 384, 24, 100), (9000, 384, 16, 50), (80000, 128, 130, 100),
                                         (2000, 256, 9, 112), (70, 384, 8, 64)])
 def test_gemm_path_large_k_bit_exact(store, n, dim, nq, k):
