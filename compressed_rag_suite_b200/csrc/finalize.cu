@@ -22,7 +22,8 @@ namespace crs {
 
 // 4 warps per query: the CTA is latency-bound (list loads, then M threads rescoring serially in fp64), so what matters
 // is how many queries are resident per SM — 128-thread CTAs fit 8+ per SM, 512-thread ones fit 2 (1024 queries: 55 -> ~15 us)
-constexpr int kFinalizeWarps = 4;
+constexpr int kFinalizeWarpsMany = 4;    // many queries: occupancy
+constexpr int kFinalizeWarpsFew = 16;    // a handful of queries: each CTA's own latency is what the caller waits for
 
 template <bool BF16>
 __device__ __forceinline__ void unpack8(const uint4& v, double (&o)[8]) {
@@ -62,7 +63,7 @@ __device__ __forceinline__ float exact_dot(const uint4* __restrict__ row, const 
     return (float)acc;
 }
 
-template <int LPL>
+template <int LPL, int kFinalizeWarps>
 __global__ void __launch_bounds__(kFinalizeWarps * 32)
 finalize_kernel(FinalizeArgs a) {
     constexpr int M = 32 * LPL;
@@ -264,18 +265,19 @@ cudaError_t launch_finalize(cudaStream_t st, const FinalizeArgs& a_in) {
     size_t smem = (a.mode == 0) ? (size_t)(M + 1) * (row_bytes + 16) : 0;
     if (smem > 110 * 1024) smem = 0;                       // wide rows x 128 candidates: read straight from HBM
     a.stage_rows = smem > 0 ? 1 : 0;
-    cudaError_t e = cudaSuccess;
-    if (a.lpl == 1) {
-        if (smem > 48 * 1024) e = cudaFuncSetAttribute(finalize_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        finalize_kernel<1><<<a.nq, kFinalizeWarps * 32, smem, st>>>(a);
-    } else if (a.lpl == 4) {
-        if (smem > 0) e = cudaFuncSetAttribute(finalize_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        finalize_kernel<4><<<a.nq, kFinalizeWarps * 32, smem, st>>>(a);
-    } else {
-        return cudaErrorInvalidValue;
-    }
+    const bool few = a.nq <= 32;
+#define CRS_FINALIZE(LPL_, NW_)                                                                                  \
+    do {                                                                                                         \
+        if (smem > 48 * 1024) {                                                                                  \
+            cudaError_t e = cudaFuncSetAttribute(finalize_kernel<LPL_, NW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) return e;                                                                      \
+        }                                                                                                        \
+        finalize_kernel<LPL_, NW_><<<a.nq, NW_ * 32, smem, st>>>(a);                                              \
+    } while (0)
+    if (a.lpl == 1) { if (few) CRS_FINALIZE(1, kFinalizeWarpsFew); else CRS_FINALIZE(1, kFinalizeWarpsMany); }
+    else if (a.lpl == 4) { if (few) CRS_FINALIZE(4, kFinalizeWarpsFew); else CRS_FINALIZE(4, kFinalizeWarpsMany); }
+    else return cudaErrorInvalidValue;
+#undef CRS_FINALIZE
     return cudaGetLastError();
 }
 

@@ -345,13 +345,13 @@ def test_gemm_sampled_start_thresholds_keep_results_exact(store):
     q[2] = x[5]
     ix = ShardIndex(dim, dtype=store)
     ix.add(x)
-    ix.set_option("sample_rows", 4096)
+    ix.set_option("sample_rows", 2048)
     for k in (10, 24):
         got = check_search(ix, x, q, store, k)
         assert ix.last_stats()["path"] == 1 and ix.last_stats()["kernel_launches"] >= 5
         ix.set_option("sample_rows", 0)
         plain = ix.search(q, k)
-        ix.set_option("sample_rows", 4096)
+        ix.set_option("sample_rows", 2048)
         assert all(np.array_equal(u, v) for u, v in zip(got, plain))
     assert list(got[0][2][:24]) == [5] + list(range(100, 123))
     check_search(ix, x, q, store, 10, min_similarity=0.3)
