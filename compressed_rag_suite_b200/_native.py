@@ -48,6 +48,7 @@ SYMBOLS = {
     "crs_mmr": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_double, _P]),
     "crs_mmr_select": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_double, _P, _P, _P, _P]),
     "crs_merge_topk": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "crs_merge_topk_strided": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, _P, _P, _P]),
     "crs_index_save": (C.c_int, [_P, C.c_char_p]),
     "crs_index_load": (C.c_int, [C.POINTER(_P), C.c_char_p, C.c_int, C.c_uint32]),
 }

@@ -796,6 +796,21 @@ int crs_merge_topk(void* cuda_stream, const uint32_t* ids, const void* scores, i
     return CRS_OK;
 }
 
+int crs_merge_topk_strided(void* cuda_stream, const uint32_t* ids, const void* scores, int is_int,
+                           int n_lists, int nq, int k_in, int k_out, int64_t list_stride,
+                           uint32_t* out_ids, void* out_scores, int32_t* out_counts) {
+    if (nq < 0 || n_lists <= 0 || k_in <= 0 || k_out <= 0 || k_out > k_in || list_stride < (int64_t)nq * k_in)
+        return fail(CRS_EINVAL, "bad sizes");
+    if (k_in > crs::kMaxListLen) return fail(CRS_EINVAL, "k_in > 128 not supported");
+    if (nq == 0) return CRS_OK;
+    if (!is_device_ptr(ids) || !is_device_ptr(scores) || !is_device_ptr(out_ids) || !is_device_ptr(out_scores) ||
+        !is_device_ptr(out_counts))
+        return fail(CRS_EINVAL, "crs_merge_topk_strided takes device buffers");
+    CRS_CUDA(crs::launch_merge_topk(reinterpret_cast<cudaStream_t>(cuda_stream), ids, scores, is_int, n_lists, nq,
+                                    k_in, k_out, out_ids, out_scores, out_counts, true, (size_t)list_stride));
+    return CRS_OK;
+}
+
 // ---- persistence: 64-byte header + raw stored rows -------------------------------------
 struct CrsFileHeader {
     char magic[8];          // "CRSIDX1\0"

@@ -104,7 +104,8 @@ cudaError_t launch_sample_tau(cudaStream_t st, const uint64_t* cand, int n_lists
 // K7: merge G lists of k_in (id, raw score) per query into the global top k_out.
 cudaError_t launch_merge_topk(cudaStream_t st, const uint32_t* ids, const void* scores, int is_int,
                               int n_lists, int nq, int k_in, int k_out,
-                              uint32_t* out_ids, void* out_scores, int32_t* out_counts, bool sorted_input = true);
+                              uint32_t* out_ids, void* out_scores, int32_t* out_counts, bool sorted_input = true,
+                              size_t list_stride = 0 /*elements between consecutive lists' [nq,k_in] blocks; 0 = nq*k_in*/);
 
 // K6: greedy MMR over m candidate vectors per query.  `fused` (optional): take the search output instead of
 // a relevance array and emit the selected hits (ids / similarity / reference score) directly.

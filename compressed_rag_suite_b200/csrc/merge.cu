@@ -16,7 +16,7 @@ constexpr int kMergeWarps = 4;
 template <int LPL, bool SORT>
 __global__ void __launch_bounds__(kMergeWarps * 32)
 merge_topk_kernel(const uint32_t* __restrict__ ids, const void* __restrict__ scores, int is_int,
-                  int n_lists, int nq, int k_in, int k_out,
+                  int n_lists, int nq, int k_in, int k_out, size_t list_stride,
                   uint32_t* __restrict__ out_ids, void* __restrict__ out_scores, int32_t* __restrict__ out_counts) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = blockIdx.x * kMergeWarps + warp;
@@ -26,7 +26,7 @@ merge_topk_kernel(const uint32_t* __restrict__ ids, const void* __restrict__ sco
     for (int s = 0; s < LPL; ++s) e[s] = 0ull;
     for (int l = 0; l < n_lists; ++l) {
         uint64_t b[LPL];
-        const size_t base = ((size_t)l * nq + q) * k_in;
+        const size_t base = (size_t)l * list_stride + (size_t)q * k_in;
 #pragma unroll
         for (int s = 0; s < LPL; ++s) {
             const int i = lane * LPL + s;
@@ -65,17 +65,19 @@ merge_topk_kernel(const uint32_t* __restrict__ ids, const void* __restrict__ sco
 
 cudaError_t launch_merge_topk(cudaStream_t st, const uint32_t* ids, const void* scores, int is_int,
                               int n_lists, int nq, int k_in, int k_out,
-                              uint32_t* out_ids, void* out_scores, int32_t* out_counts, bool sorted_input) {
+                              uint32_t* out_ids, void* out_scores, int32_t* out_counts, bool sorted_input,
+                              size_t list_stride) {
     if (nq <= 0) return cudaSuccess;
+    if (list_stride == 0) list_stride = (size_t)nq * k_in;
     if (k_in > kMaxListLen || k_out > k_in || k_out <= 0 || n_lists <= 0) return cudaErrorInvalidValue;
     const int grid = (nq + kMergeWarps - 1) / kMergeWarps;
     const int threads = kMergeWarps * 32;
     if (sorted_input) {
-        if (k_in <= 32) merge_topk_kernel<1, false><<<grid, threads, 0, st>>>(ids, scores, is_int, n_lists, nq, k_in, k_out, out_ids, out_scores, out_counts);
-        else            merge_topk_kernel<4, false><<<grid, threads, 0, st>>>(ids, scores, is_int, n_lists, nq, k_in, k_out, out_ids, out_scores, out_counts);
+        if (k_in <= 32) merge_topk_kernel<1, false><<<grid, threads, 0, st>>>(ids, scores, is_int, n_lists, nq, k_in, k_out, list_stride, out_ids, out_scores, out_counts);
+        else            merge_topk_kernel<4, false><<<grid, threads, 0, st>>>(ids, scores, is_int, n_lists, nq, k_in, k_out, list_stride, out_ids, out_scores, out_counts);
     } else {
-        if (k_in <= 32) merge_topk_kernel<1, true><<<grid, threads, 0, st>>>(ids, scores, is_int, n_lists, nq, k_in, k_out, out_ids, out_scores, out_counts);
-        else            merge_topk_kernel<4, true><<<grid, threads, 0, st>>>(ids, scores, is_int, n_lists, nq, k_in, k_out, out_ids, out_scores, out_counts);
+        if (k_in <= 32) merge_topk_kernel<1, true><<<grid, threads, 0, st>>>(ids, scores, is_int, n_lists, nq, k_in, k_out, list_stride, out_ids, out_scores, out_counts);
+        else            merge_topk_kernel<4, true><<<grid, threads, 0, st>>>(ids, scores, is_int, n_lists, nq, k_in, k_out, list_stride, out_ids, out_scores, out_counts);
     }
     return cudaGetLastError();
 }

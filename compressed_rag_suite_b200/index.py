@@ -105,6 +105,17 @@ class ShardIndex:
         N.check(self._lib.crs_index_add(self._h, a.ctypes.data_as(C.c_void_p), a.shape[0], N.CRS_F32))
 
     # ------------------------------------------------------------------ search
+    def search_into(self, queries, k: int, min_similarity, ids, scores, counts) -> None:
+        """Device-buffer search writing into caller-provided CUDA tensors (ids int32 [nq,k], scores
+        f32|i32 [nq,k] — any 32-bit dtype view —, counts int32 [nq]); enqueued on the current stream."""
+        q = queries.contiguous()
+        if q.dim() == 1:
+            q = q[None, :]
+        self._use_torch_stream()
+        N.check(self._lib.crs_index_search(self._h, C.c_void_p(q.data_ptr()), q.shape[0], int(k), float(min_similarity),
+                                           C.c_void_p(ids.data_ptr()), C.c_void_p(scores.data_ptr()),
+                                           C.c_void_p(counts.data_ptr())))
+
     def search(self, queries, k: int, min_similarity: float = -math.inf, allow=None, out=None):
         """-> (ids uint32 [nq,k], raw scores f32|i32 [nq,k], counts i32 [nq]).
 
@@ -369,6 +380,23 @@ def select_topk(ids, scores, k_out: int):
     N.check(N.lib().crs_select_topk(C.c_void_p(st), C.c_void_p(ids.data_ptr()), C.c_void_p(scores.data_ptr()),
                                     int(is_int), nq, m, int(k_out), C.c_void_p(out_ids.data_ptr()),
                                     C.c_void_p(out_sc.data_ptr()), C.c_void_p(out_cnt.data_ptr())))
+    return out_ids, out_sc, out_cnt
+
+
+def merge_gathered(gathered, nq: int, k_in: int, k_out: int, is_int: bool):
+    """K7 straight out of an allgathered buffer: `gathered` int32 CUDA [G, 2, nq, k_in] where [:, 0] are
+    the ranks' id blocks and [:, 1] their raw-score bits -> (ids, scores, counts); no copies."""
+    import torch
+    g = gathered.shape[0]
+    dev = gathered.device
+    out_ids = torch.empty((nq, k_out), dtype=torch.int32, device=dev)
+    out_sc = torch.empty((nq, k_out), dtype=torch.int32 if is_int else torch.float32, device=dev)
+    out_cnt = torch.empty((nq,), dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    base = gathered.data_ptr()
+    N.check(N.lib().crs_merge_topk_strided(C.c_void_p(st), C.c_void_p(base), C.c_void_p(base + nq * k_in * 4), int(is_int),
+                                           g, nq, k_in, int(k_out), 2 * nq * k_in, C.c_void_p(out_ids.data_ptr()),
+                                           C.c_void_p(out_sc.data_ptr()), C.c_void_p(out_cnt.data_ptr())))
     return out_ids, out_sc, out_cnt
 
 

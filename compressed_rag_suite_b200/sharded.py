@@ -69,15 +69,20 @@ class ShardedSearcher:
     def search(self, queries, k: int, min_similarity: float = -math.inf):
         """queries: float32 CUDA tensor [nq, dim], the same on every rank.
         -> (ids int32 bit patterns [nq,k], raw scores [nq,k], counts [nq]) CUDA tensors."""
-        from .index import merge_topk
-        ids, sc, cnt = self.index.search(queries, k, min_similarity)
+        import torch
+        from .index import merge_gathered
         if self.world == 1:
             self.merge_launches = 0
-            return ids, sc, cnt
-        gathered = exchange_candidates(pack_candidates(ids, sc), self.group)
-        g_ids, g_sc = unpack_candidates(gathered, self.index.is_int)
+            return self.index.search(queries, k, min_similarity)
+        # the local result is written straight into the send buffer ([0] ids, [1] raw-score bits) and the
+        # merge reads the gathered buffer in place: search -> allgather -> merge, no pack / unpack copies
+        nq = queries.shape[0] if queries.dim() > 1 else 1
+        send = torch.empty((2, nq, k), dtype=torch.int32, device=queries.device)
+        cnt = torch.empty((nq,), dtype=torch.int32, device=queries.device)
+        self.index.search_into(queries, k, min_similarity, send[0], send[1], cnt)
+        gathered = exchange_candidates(send, self.group)             # [G, 2, nq, k]
         self.merge_launches = 1
-        return merge_topk(g_ids, g_sc, k)
+        return merge_gathered(gathered, nq, k, k, self.index.is_int)
 
 
 # ------------------------------------------------------------------------------------------

@@ -170,6 +170,13 @@ int crs_merge_topk(void* cuda_stream, const uint32_t* ids, const void* scores, i
                    int n_lists, int nq, int k_in, int k_out,
                    uint32_t* out_ids, void* out_scores, int32_t* out_counts);
 
+/* the same when rank l's [nq, k_in] block starts `list_stride` elements after rank l-1's (ids and
+ * scores alike): lets each rank allgather ONE buffer holding its ids block followed by its scores
+ * block and merge straight out of the gathered buffer, with no pack / unpack copies. */
+int crs_merge_topk_strided(void* cuda_stream, const uint32_t* ids, const void* scores, int is_int,
+                           int n_lists, int nq, int k_in, int k_out, int64_t list_stride,
+                           uint32_t* out_ids, void* out_scores, int32_t* out_counts);
+
 /* replaces chromadb.PersistentClient(path) persistence + get_collection reload —
  * rag/indexing.py:32-34,46-55.  Raw code blob + small header; the host keeps
  * ids/documents/metadatas in a sidecar. */

@@ -40,6 +40,11 @@ def _worker(rank, world, port, store, n, k, out_dir):
         gathered = exchange_candidates(packed)                                       # the one collective
         assert gathered.shape == (world, 6, k, 2)
         g_ids, g_sc = unpack_candidates(gathered, store in ("i8", "b1"))
+        # the product's send layout: one [2, nq, k] buffer (ids block, then raw-score bits), merged in place
+        send = torch.stack((torch.from_numpy(ids.view(np.int32)), torch.from_numpy(raw).view(torch.int32)))
+        g2 = exchange_candidates(send)
+        assert g2.shape == (world, 2, 6, k)
+        assert torch.equal(g2[:, 0], g_ids) and torch.equal(g2[:, 1], g_sc.view(torch.int32))
         m = search.merge_topk(g_ids.numpy().view(np.uint32), g_sc.numpy(), k)
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), ids=m[0], raw=m[1], cnt=m[2])
     finally:
