@@ -97,6 +97,7 @@ struct crs_index {
     int force_path = -1;
     int force_exact = 0;
     int gemm_cluster = 0;
+    int gemm_prefetch = 0;      // corpus tiles prefetched into L2 ahead of the TMA ring (0 = off)
     int64_t sample_rows = 65536; // rows of the sample pass that seeds the contraction's per-query thresholds (0 = off)
     int short_lists = 1;        // integer scans with k > 32 keep 32 keys per CTA + certification (0 = full 128-key lists)
     int multi_scan = 8;         // largest group of short-row integer queries that shares one corpus pass (<= 1: off)
@@ -255,6 +256,7 @@ int crs_index_set_option(crs_index* ix, const char* name, int64_t value) {
     else if (!strcmp(name, "force_exact")) ix->force_exact = (int)value;
     else if (!strcmp(name, "gemm_cluster")) ix->gemm_cluster = (int)value;
     else if (!strcmp(name, "gemm_min_nq")) ix->gemm_min_nq = (int)value;
+    else if (!strcmp(name, "gemm_prefetch")) ix->gemm_prefetch = (int)value;
     else if (!strcmp(name, "multi_scan")) ix->multi_scan = (int)value;
     else if (!strcmp(name, "short_lists")) ix->short_lists = (int)value;
     else if (!strcmp(name, "sample_rows")) ix->sample_rows = value;
@@ -520,7 +522,8 @@ static int search_impl(crs_index* ix, const void* queries, int nq, int k, float 
                     if (is_float) fa.tau_q = tau_q;
                 }
                 CRS_CUDA(crs::launch_gemm_topk(st, ix->codes, ix->count, (int)ix->row_bytes, kind, ix->qcodes.p, nq, k,
-                                               tau_bits, ix->cand.p, ix->num_sms, ix->gemm_cluster, &n_slices, plan.allow, tau_q));
+                                               tau_bits, ix->cand.p, ix->num_sms, ix->gemm_cluster, &n_slices, plan.allow, tau_q,
+                                               ix->gemm_prefetch));
                 ++launches;
                 fa.n_lists = n_slices;
                 fa.list_len = crs::gemm_list_len(k);

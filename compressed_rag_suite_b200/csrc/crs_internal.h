@@ -96,7 +96,8 @@ cudaError_t launch_gemm_topk(cudaStream_t st, const void* codes, int64_t n, int 
                              const void* qcodes, int nq, int k, uint32_t tau_pre_bits, uint64_t* cand, int num_sms,
                              int cluster /*0 = auto, else 1|2|4 query tiles per multicast cluster*/, int* n_slices_out,
                              const uint32_t* allow /*optional row bitmap, applied to epilogue hits*/,
-                             const uint32_t* tau_q = nullptr /*optional [nq] per-query starting thresholds (score bits)*/);
+                             const uint32_t* tau_q = nullptr /*optional [nq] per-query starting thresholds (score bits)*/,
+                             int prefetch_tiles = 0 /*corpus tiles the producer prefetches into L2 ahead of its ring*/);
 // per-query starting thresholds from the lists of a sample pass (L-th best key minus margin_rel * |q|)
 cudaError_t launch_sample_tau(cudaStream_t st, const uint64_t* cand, int n_lists, int list_len, int nq, int is_int,
                               const float* qnorms, float margin_rel, uint32_t* tau_q);

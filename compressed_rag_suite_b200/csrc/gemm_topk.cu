@@ -59,6 +59,12 @@ __device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap
         "[%0], [%1, {%3, %4}], [%2], %5;"
         ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
 }
+// L2 prefetch of one TMA box (no shared memory, no barrier): issued a couple of corpus tiles ahead so the
+// ring's own loads find their data in L2 — half of them used to go to DRAM (ncu: 51 % L2 hit rate) with
+// a latency the 4-stage ring cannot cover.
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -201,14 +207,18 @@ __device__ __forceinline__ void slab_scan(const uint32_t (&r)[32], int64_t row0,
                                           typename ScoreT<INT>::type tau_pre, typename ScoreT<INT>::type& tau,
                                           uint64_t (&best)[L], const uint32_t* __restrict__ allow) {
     using T = typename ScoreT<INT>::type;
-    T m[16];
+    // maximum of the 32 scores as a tree of 3-input max (FMNMX3 / VIMNMX3 on sm_100): 16 instructions
+    T m[11];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) m[i] = smax<T>(score_of<INT>(r[2 * i]), score_of<INT>(r[2 * i + 1]));
-#pragma unroll
-    for (int w = 8; w >= 1; w >>= 1) {
-#pragma unroll
-        for (int i = 0; i < w; ++i) m[i] = smax<T>(m[i], m[i + w]);
-    }
+    for (int i = 0; i < 10; ++i)
+        m[i] = smax<T>(smax<T>(score_of<INT>(r[3 * i]), score_of<INT>(r[3 * i + 1])), score_of<INT>(r[3 * i + 2]));
+    m[10] = smax<T>(score_of<INT>(r[30]), score_of<INT>(r[31]));
+    m[0] = smax<T>(smax<T>(m[0], m[1]), m[2]);
+    m[3] = smax<T>(smax<T>(m[3], m[4]), m[5]);
+    m[6] = smax<T>(smax<T>(m[6], m[7]), m[8]);
+    m[9] = smax<T>(m[9], m[10]);
+    m[0] = smax<T>(smax<T>(m[0], m[3]), m[6]);
+    m[0] = smax<T>(m[0], m[9]);
     if (m[0] >= tau) {
         unsigned mask = 0;
         T tmp[32];                           // dynamically indexed -> local memory, touched on this path only
@@ -240,7 +250,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
                  int64_t n_rows, int n_qtiles, int n_slices, uint32_t idesc, uint32_t tau_pre_bits,
                  uint64_t* __restrict__ cand, int nq, int list_stride, const uint32_t* __restrict__ allow,
-                 const uint32_t* __restrict__ tau_q) {
+                 const uint32_t* __restrict__ tau_q, int prefetch_tiles) {
     static_assert(!PAIR || CS == 2, "the CTA-pair MMA needs clusters of exactly two CTAs");
     // pair mode: a stage holds this CTA's half (128 rows) of a corpus chunk -> twice the stages in the same smem
     constexpr int STAGES = PAIR ? 2 * kStages : kStages;
@@ -294,6 +304,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 int stage = 0; uint32_t phase = 0;
                 for (int t = 0; t < n_tiles; ++t) {
                     const int row0 = (int)((tile_lo + t) * kTileC) + crank * (kTileC / 2);
+                    if (prefetch_tiles > 0 && t + prefetch_tiles < n_tiles)
+                        for (int kc = 0; kc < KCH; ++kc)
+                            tma_prefetch_2d(&map_c, kc * (INT ? 128 : kChunkK), row0 + prefetch_tiles * kTileC);
                     for (int kc = 0; kc < KCH; ++kc) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * BSTAGE);
@@ -309,6 +322,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             int stage = 0; uint32_t phase = 0;
             for (int t = 0; t < n_tiles; ++t) {
                 const int row0 = (int)((tile_lo + t) * kTileC);
+                if (prefetch_tiles > 0 && t + prefetch_tiles < n_tiles) {   // this CTA's piece of a tile ahead -> L2
+                    const int prow = (int)((tile_lo + t + prefetch_tiles) * kTileC) + crank * (kTileC / CS);
+                    for (int kc = 0; kc < KCH; ++kc) tma_prefetch_2d(&map_c, kc * (INT ? 128 : kChunkK), prow);
+                }
                 for (int kc = 0; kc < KCH; ++kc) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full_bar[stage], kBStageBytes);      // all CS pieces land here
@@ -529,7 +546,7 @@ static bool make_map(CUtensorMap* map, const void* base, int64_t rows, int row_b
 template <int KCH, int L, int CS, bool INT, bool PAIR>
 static cudaError_t launch_kch(cudaStream_t st, const CUtensorMap& mq, const CUtensorMap& mc, int64_t n, int n_qtiles,
                               int n_slices, uint32_t idesc, uint32_t tau_pre, uint64_t* cand, int nq, int list_stride,
-                              const uint32_t* allow, const uint32_t* tau_q) {
+                              const uint32_t* allow, const uint32_t* tau_q, int prefetch_tiles) {
     const size_t smem = (size_t)KCH * kAChunkBytes + (size_t)kStages * kBStageBytes + 1024;
     auto kern = gemm_topk_kernel<KCH, L, CS, INT, PAIR>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -546,20 +563,20 @@ static cudaError_t launch_kch(cudaStream_t st, const CUtensorMap& mq, const CUte
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, list_stride, allow, tau_q);
+    return cudaLaunchKernelEx(&cfg, kern, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, list_stride, allow, tau_q, prefetch_tiles);
 }
 
 template <int KCH, int L, bool INT>
 static cudaError_t launch_cs(int cs, cudaStream_t st, const CUtensorMap& mq, const CUtensorMap& mc, int64_t n,
                              int n_qtiles, int n_slices, uint32_t idesc, uint32_t tau_pre, uint64_t* cand, int nq,
-                             const uint32_t* allow, const uint32_t* tau_q) {
+                             const uint32_t* allow, const uint32_t* tau_q, int prefetch_tiles) {
     if (cs == 22) {     // CTA pair: M = 256 across the two SMs of a cluster
         const uint32_t idesc_pair = (idesc & ~(0x1Fu << 24)) | ((uint32_t)(2 * kTileQ >> 4) << 24);
-        return launch_kch<KCH, L, 2, INT, true>(st, mq, mc, n, n_qtiles, n_slices, idesc_pair, tau_pre, cand, nq, 32, allow, tau_q);
+        return launch_kch<KCH, L, 2, INT, true>(st, mq, mc, n, n_qtiles, n_slices, idesc_pair, tau_pre, cand, nq, 32, allow, tau_q, prefetch_tiles);
     }
-    if (cs == 4) return launch_kch<KCH, L, 4, INT, false>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32, allow, tau_q);
-    if (cs == 2) return launch_kch<KCH, L, 2, INT, false>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32, allow, tau_q);
-    return launch_kch<KCH, L, 1, INT, false>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32, allow, tau_q);
+    if (cs == 4) return launch_kch<KCH, L, 4, INT, false>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32, allow, tau_q, prefetch_tiles);
+    if (cs == 2) return launch_kch<KCH, L, 2, INT, false>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32, allow, tau_q, prefetch_tiles);
+    return launch_kch<KCH, L, 1, INT, false>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32, allow, tau_q, prefetch_tiles);
 }
 
 // kind: 0 fp16, 1 bf16, 2 int8
@@ -572,7 +589,8 @@ int gemm_list_len(int k) { return k <= 10 ? 16 : 32; }
 
 cudaError_t launch_gemm_topk(cudaStream_t st, const void* codes, int64_t n, int row_bytes, int kind,
                              const void* qcodes, int nq, int k, uint32_t tau_pre_bits, uint64_t* cand, int num_sms,
-                             int cluster, int* n_slices_out, const uint32_t* allow, const uint32_t* tau_q) {
+                             int cluster, int* n_slices_out, const uint32_t* allow, const uint32_t* tau_q,
+                             int prefetch_tiles) {
     const int kch = row_bytes / 128;
     int n_qtiles = (nq + kTileQ - 1) / kTileQ;
     // cluster size: query tiles that share one corpus stream through TMA multicast
@@ -599,10 +617,10 @@ cudaError_t launch_gemm_topk(cudaStream_t st, const void* codes, int64_t n, int 
 #define CRS_GEMM_CASE(KCH_)                                                                                              \
     case KCH_:                                                                                                           \
         if (kind == 2)                                                                                                   \
-            return L == 16 ? launch_cs<KCH_, 16, true>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq, allow, tau_q)   \
-                           : launch_cs<KCH_, 32, true>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq, allow, tau_q);  \
-        return L == 16 ? launch_cs<KCH_, 16, false>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq, allow, tau_q)      \
-                       : launch_cs<KCH_, 32, false>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq, allow, tau_q);
+            return L == 16 ? launch_cs<KCH_, 16, true>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq, allow, tau_q, prefetch_tiles)   \
+                           : launch_cs<KCH_, 32, true>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq, allow, tau_q, prefetch_tiles);  \
+        return L == 16 ? launch_cs<KCH_, 16, false>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq, allow, tau_q, prefetch_tiles)      \
+                       : launch_cs<KCH_, 32, false>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq, allow, tau_q, prefetch_tiles);
     switch (kch) {
         CRS_GEMM_CASE(1)
         CRS_GEMM_CASE(2)

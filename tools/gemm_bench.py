@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from compressed_rag_suite_b200.index import ShardIndex
 
-def run(n, dim, nq, k, iters=10, store="f16", cluster=0, warm=3):
+def run(n, dim, nq, k, iters=10, store="f16", cluster=0, warm=3, prefetch=(0,), sample=(65536,)):
     ix = ShardIndex(dim, dtype=store, reserve_rows=n)
     g = torch.Generator(device="cuda"); g.manual_seed(0)
     cen = torch.randn(4096, dim, device="cuda", generator=g); cen /= cen.norm(dim=1, keepdim=True)
@@ -18,35 +18,29 @@ def run(n, dim, nq, k, iters=10, store="f16", cluster=0, warm=3):
     q = 0.6 * cen[torch.randint(0, 4096, (nq,), device="cuda", generator=g)] + 0.8 * z
     ix.set_option("profiling", 1)
     ix.set_option("gemm_cluster", cluster)
-    for _ in range(warm):
-        ix.search(q, k)
-    torch.cuda.synchronize()
-    ts, ks = [], []
-    for _ in range(iters):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); ix.search(q, k); b.record(); torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b)); ks.append(ix.last_kernel_ms())
-    ts.sort(); ks.sort()
-    st = ix.last_stats()
-    flops = 2.0 * ((nq + 127) // 128 * 128) * n * ix.dim_padded
-    print(json.dumps({"cluster": cluster, "n": n, "dim": dim, "nq": nq, "k": k, "path": st["path"], "ms_med": round(ts[len(ts)//2], 3),
-                      "kernel_ms_med": round(ks[len(ks)//2], 3), "qps": round(nq / ts[len(ts)//2] * 1e3),
-                      "TFLOPs_kernel": round(flops / ks[len(ks)//2] / 1e9, 1), "GBps_kernel": round(n * ix.row_bytes / ks[len(ks)//2] / 1e6, 1),
-                      "launches": st["kernel_launches"], "grid": st["grid"], "uncert": st["uncertified_total"]}), flush=True)
+    for pf in prefetch:
+      for smp in sample:
+        ix.set_option("gemm_prefetch", pf)
+        ix.set_option("sample_rows", smp)
+        for _ in range(warm):
+            ix.search(q, k)
+        torch.cuda.synchronize()
+        ts, ks = [], []
+        for _ in range(iters):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); ix.search(q, k); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b)); ks.append(ix.last_kernel_ms())
+        ts.sort(); ks.sort()
+        st = ix.last_stats()
+        flops = 2.0 * ((nq + 127) // 128 * 128) * n * ix.dim_padded
+        print(json.dumps({"cluster": cluster, "prefetch": pf, "sample": smp, "n": n, "dim": dim, "nq": nq, "k": k, "store": store, "ms_med": round(ts[len(ts)//2], 3),
+                          "kernel_ms_med": round(ks[len(ks)//2], 3), "qps": round(nq / ts[len(ts)//2] * 1e3),
+                          "TFLOPs_kernel": round(flops / ks[len(ks)//2] / 1e9, 1),
+                          "launches": st["kernel_launches"], "uncert": st["uncertified_total"]}), flush=True)
     ix.close()
 
 if __name__ == "__main__":
-    import sys
-    if len(sys.argv) > 1 and sys.argv[1] == "burst":
-        for cl in (2, 22, 2, 22):
-            run(10_000_000, 384, 1024, 10, cluster=cl, iters=10, warm=3)
-            import time; time.sleep(3)
-        sys.exit(0)
-    # sustained (power-capped) numbers: 150 warm-up batches (~1 s of load) before timing
-    for cl in (2, 22, 2, 22):
-        run(10_000_000, 384, 1024, 10, cluster=cl, iters=40, warm=150)
-    for cl in (2, 22):
-        run(10_000_000, 384, 1024, 10, store="i8", cluster=cl, iters=40, warm=150)
-    run(10_000_000, 384, 1024, 100, cluster=22, iters=20, warm=20)
-    run(1_250_000, 384, 1024, 10, cluster=2, iters=20, warm=20)
-    run(1_250_000, 384, 1024, 10, cluster=22, iters=20, warm=20)
+    # A/B on one box, sustained (power-capped) clocks: every variant after ~1 s of load
+    run(10_000_000, 384, 1024, 10, cluster=2, iters=30, warm=120, prefetch=(0, 2, 4, 0, 2), sample=(65536,))
+    run(10_000_000, 384, 1024, 10, cluster=2, iters=30, warm=120, prefetch=(0,), sample=(0, 65536))
+    run(1_250_000, 384, 1024, 10, cluster=2, iters=30, warm=50, prefetch=(0, 2), sample=(0, 65536))
