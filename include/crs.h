@@ -102,9 +102,18 @@ int crs_index_search_filtered(crs_index* idx, const void* queries, int nq, int k
                               const uint32_t* allow_bits, uint32_t* out_ids, void* out_scores,
                               int32_t* out_counts);
 int crs_index_last_stats(const crs_index* idx, crs_search_stats* out);
-/* Tuning / test hooks: name in {"force_path" (-1 auto, 0 scan, 1 gemm), "force_exact"
- * (1 = always run the fp64 pass), "eps_scale" (x1000), "profiling" (1 = bracket the
- * dominant kernel(s) of each search with CUDA events on the index's stream)}. */
+/* Tuning / test hooks (defaults in brackets):
+ *   "force_path"    [-1] -1 auto, 0 stream scans (K1-K3), 1 tensor-core contraction (K4/K5)
+ *   "gemm_min_nq"   [2]  smallest batch that takes the contraction
+ *   "gemm_cluster"  [0]  0 auto (2 query tiles per TMA-multicast cluster), 1 | 2 | 4, 22 = CTA-pair MMA (cta_group::2)
+ *   "gemm_prefetch" [0]  corpus tiles prefetched into L2 ahead of the TMA ring
+ *   "sample_rows"   [65536] rows of the sample pass that seeds the contraction's per-query thresholds (0 = off)
+ *   "multi_scan"    [8]  largest group of short-row integer queries that shares one corpus pass (<= 1 = off)
+ *   "short_lists"   [1]  integer scans with k > 32 keep 32 keys per CTA + certification (0 = full 128-key lists)
+ *   "force_exact"   [0]  1 = skip the fast pass of float stores, always run the exhaustive fp64 pass
+ *   "eps_scale"     [1000] certification error bound x value/1000
+ *   "profiling"     [0]  1 = bracket the dominant kernel(s) of each search with CUDA events on the index's stream
+ * None of them changes a result: every combination returns the canonical top-k (tests compare them). */
 int crs_index_set_option(crs_index* idx, const char* name, int64_t value);
 /* device time of the dominant kernel(s) (scan passes or GEMM) of the last search, from the
  * CUDA events recorded when "profiling" is on; waits for that search to finish. */
