@@ -70,3 +70,28 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f"{f} imports the oracle"
+
+
+def _build_c_example(tmp_path):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(str(tmp_path), "crs_example")
+    libdir = os.path.join(root, "compressed_rag_suite_b200")
+    out = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(root, "include"),
+                          os.path.join(root, "examples", "crs_example.c"), "-o", exe, "-L" + libdir, "-lcrs",
+                          "-Wl,-rpath," + libdir, "-lm"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    return exe
+
+
+def test_header_is_plain_c_and_a_c_host_links_and_fails_loudly_without_gpu(tmp_path):
+    """include/crs.h compiles as strict C99 from a C caller; with no GPU the program reports
+    CRS_ECUDA from crs_index_create instead of computing anything on the CPU."""
+    import subprocess
+    import torch
+    exe = _build_c_example(tmp_path)
+    run = subprocess.run([exe], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert run.returncode == 0 and run.stdout.strip().endswith("ok"), run.stdout + run.stderr
+    else:
+        assert run.returncode == 2 and "no CPU implementation" in run.stderr

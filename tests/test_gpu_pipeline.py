@@ -187,3 +187,18 @@ def test_where_filters_equal_oracle_chroma():
     out = r.retrieve("find alpha", filters={"page_number": 5})
     assert len(out) == 3 and all(c["metadata"]["page_number"] == 5 for c in out)
     assert r.retrieve_batch(["find alpha"], filters={"page_number": 5}) == [out]
+
+
+def test_plain_c_host_runs_a_search(tmp_path):
+    """examples/crs_example.c: a C99 program indexes 4096 rows and finds row 123 by its own vector."""
+    import subprocess
+    sys_path_root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(sys_path_root, "compressed_rag_suite_b200")
+    exe = os.path.join(str(tmp_path), "crs_example")
+    b = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(sys_path_root, "include"),
+                        os.path.join(sys_path_root, "examples", "crs_example.c"), "-o", exe, "-L" + libdir, "-lcrs",
+                        "-Wl,-rpath," + libdir, "-lm"], capture_output=True, text=True)
+    assert b.returncode == 0, b.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
+    assert "rank 0: row 123" in r.stdout
