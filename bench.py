@@ -26,6 +26,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+EMIT = print        # replaced in __main__ by a writer that owns the real stdout
 METRIC = "exact top-k QPS @10Mx384 fp16 (1024-query batch, top-10)"
 UNIT = "queries/s"
 N_CLUSTERS = 4096
@@ -81,7 +82,7 @@ def run_reference(a):
     cores = cb.host_threads()
     sample_txt = (f"{sample}-row slice x {a.batch} queries per step, numpy/OpenBLAS fp32 matmul + argpartition, "
                   f"time scaled x{scale:g} to {a.rows} rows (linear extrapolation)")
-    print(json.dumps({
+    EMIT(json.dumps({
         "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic clustered unit-norm embeddings (numpy stream)",
@@ -89,7 +90,7 @@ def run_reference(a):
         "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_txt},
         "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference engine is chromadb==1.3.0 (not installable offline); this arm is the oracle's CPU port of its exhaustive cosine search",
-    }), flush=True)
+    }))
 
 
 # ---------------------------------------------------------------------------- data (device)
@@ -356,14 +357,39 @@ def run_ours(a):
         out["cpu_baseline"] = {"value": a.batch / (per * scale), "unit": UNIT, "cores": cb.host_threads(), "kind": "port",
                                "sample": f"{sample}-row slice x {a.batch} queries, numpy/OpenBLAS fp32 matmul + top-k, "
                                          f"3 timed passes, time scaled x{scale:g} to {a.rows} rows"}
-    print(json.dumps(out), flush=True)
+    EMIT(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
+class _StdoutToStderr:
+    """Everything libraries write to fd 1 while the bench runs (e.g. NCCL's version banner) goes to
+    stderr, so stdout carries exactly the one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        print(line, flush=True)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 if __name__ == "__main__":
     args = parse()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    with _StdoutToStderr() as _out:
+        EMIT = _out.emit
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
