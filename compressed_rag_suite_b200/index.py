@@ -191,6 +191,7 @@ class ShardIndex:
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             ids, sc, cnt = self.search(q, k, min_similarity)
+        self._use_torch_stream()                           # the capture stream is gone: back to the caller's stream
         return GraphedSearch(graph, q, ids, sc, cnt, len(self))
 
     def pack_allow(self, allow) -> np.ndarray:
