@@ -34,6 +34,11 @@ def run(n, dim, nq, k, store, cluster):
     ix.close()
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "shard":          # the per-GPU work of the 8-GPU headline run
+        run(1_250_000, 384, 1024, 10, "f16", 2)
+        run(1_250_000, 384, 1024, 10, "i8", 2)
+        run(10_000_000, 384, 1024, 10, "f16", 2)
+        sys.exit(0)
     run(10_000_000, 384, 1024, 10, "f16", 2)
     run(10_000_000, 384, 1024, 10, "f16", 22)
     run(10_000_000, 384, 1024, 10, "i8", 2)
