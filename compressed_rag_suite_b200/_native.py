@@ -49,6 +49,16 @@ SYMBOLS = {
     "crs_mmr_select": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_double, _P, _P, _P, _P]),
     "crs_merge_topk": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "crs_merge_topk_strided": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, _P, _P, _P]),
+    "crs_exchange_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "crs_exchange_destroy": (C.c_int, [_P]),
+    "crs_exchange_ipc_handle": (C.c_int, [_P, _P]),
+    "crs_exchange_open_peers": (C.c_int, [_P, _P]),
+    "crs_exchange_buffer": (C.c_int, [_P, C.POINTER(_P)]),
+    "crs_exchange_set_peer_buffers": (C.c_int, [_P, C.POINTER(_P)]),
+    "crs_exchange_status": (C.c_int, [_P, _P, C.POINTER(C.c_int), C.POINTER(C.c_uint32)]),
+    "crs_index_search_sharded": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_float, _P, _P, _P]),
+    "crs_index_search_push": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_float]),
+    "crs_exchange_merge": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "crs_index_save": (C.c_int, [_P, C.c_char_p]),
     "crs_index_load": (C.c_int, [C.POINTER(_P), C.c_char_p, C.c_int, C.c_uint32]),
 }

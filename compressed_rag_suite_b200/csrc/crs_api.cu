@@ -63,6 +63,16 @@ size_t row_bytes_for(int dim_padded, crs_dtype store) {
     }
 }
 
+// temporary device buffer of one call: freed on every return path (cudaFree waits for pending work)
+struct DevTmp {
+    void* p = nullptr;
+    DevTmp() = default;
+    DevTmp(const DevTmp&) = delete;
+    DevTmp& operator=(const DevTmp&) = delete;
+    ~DevTmp() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes); }
+};
+
 template <typename T>
 struct DevScratch {
     T* p = nullptr;
@@ -98,7 +108,9 @@ struct crs_index {
     int force_exact = 0;
     int gemm_cluster = 0;
     int gemm_prefetch = 0;      // corpus tiles prefetched into L2 ahead of the TMA ring (0 = off)
-    int64_t sample_rows = 65536; // rows of the sample pass that seeds the contraction's per-query thresholds (0 = off)
+    int64_t sample_rows = 0;    // rows of an optional sample pass that seeds the contraction's per-query floors (0 = off)
+    int share_floor = 1;        // contraction: the slices of a query share their k-th best score while the launch runs
+    int gemm_warm = 8;          // contraction: first tiles of every slice that only seed the floor and are redone last
     int short_lists = 1;        // integer scans with k > 32 keep 32 keys per CTA + certification (0 = full 128-key lists)
     int multi_scan = 8;         // largest group of short-row integer queries that shares one corpus pass (<= 1: off)
     int gemm_min_nq = 2;        // batches of at least this many queries take the tensor-core path: one corpus read for
@@ -111,14 +123,28 @@ struct crs_index {
     DevScratch<int32_t> flags, counts_dev;
     DevScratch<uint32_t> ids_dev;
     DevScratch<uint8_t> scores_dev;
-    DevScratch<uint32_t> allow_dev, tauq;
+    DevScratch<uint32_t> allow_dev, floors;     // floors: [tau_q (nq, padded to 128) | pub lists] of the contraction
     int32_t* n_flagged = nullptr;      // device counters: [0] uncertified this search, [1] since create,
                                        // [2] float bits of the largest |fast - exact| score seen in finalize
     crs_search_stats stats{};
     int profiling = 0;
+    cudaEvent_t ev_switch = nullptr;           // orders a newly set stream after the previous one
     cudaEvent_t evs[32][2] = {};               // ring of event pairs bracketing the dominant kernel(s) of each search
     int64_t ev_count = 0;                      // searches timed so far
     std::mutex mu;
+};
+
+// Peer-memory exchange of one rank (exchange.cu): its receive buffer, the mapped buffers of its peers, the
+// step stamp and the staging area the local search writes its [nq, k] result into.
+struct crs_exchange {
+    int device = 0, rank = 0, world = 1, max_nq = 0, max_k = 0, flag_ctas = 0;
+    size_t slots_words = 0, flags_words = 0;
+    uint32_t* buf = nullptr;                       // receive buffer: [slots | flags], cudaMalloc'ed and zeroed
+    uint32_t* ctl = nullptr;                       // [0] step stamp, [1] error word
+    uint32_t* local = nullptr;                     // [ids (max_nq*max_k) | scores (max_nq*max_k) | counts (max_nq)]
+    void* peers[crs::kMaxWorld] = {};              // every rank's receive buffer as seen from this device (own = buf)
+    bool ipc_opened[crs::kMaxWorld] = {};
+    bool wired = false;
 };
 
 namespace {
@@ -136,9 +162,12 @@ int grow(crs_index* ix, int64_t need) {
     cap = std::max<int64_t>(cap, 1024);
     uint8_t* p = nullptr;
     CRS_CUDA(cudaMalloc(&p, (size_t)cap * ix->row_bytes));
+    cudaError_t e = cudaSuccess;
     if (ix->count > 0)
-        CRS_CUDA(cudaMemcpyAsync(p, ix->codes, (size_t)ix->count * ix->row_bytes, cudaMemcpyDeviceToDevice, ix->stream));
-    if (ix->codes) { CRS_CUDA(cudaStreamSynchronize(ix->stream)); cudaFree(ix->codes); }
+        e = cudaMemcpyAsync(p, ix->codes, (size_t)ix->count * ix->row_bytes, cudaMemcpyDeviceToDevice, ix->stream);
+    if (e == cudaSuccess && ix->codes) e = cudaStreamSynchronize(ix->stream);
+    if (e != cudaSuccess) { cudaFree(p); return cuda_fail(e, "grow"); }
+    if (ix->codes) cudaFree(ix->codes);
     ix->codes = p;
     ix->capacity = cap;
     return CRS_OK;
@@ -196,6 +225,10 @@ int crs_index_create(crs_index** out, int dim, crs_dtype store, crs_metric metri
     if (store != CRS_F16 && store != CRS_BF16 && store != CRS_I8 && store != CRS_B1)
         return fail(CRS_EINVAL, "store dtype must be F16, BF16, I8 or B1");
     if (metric != CRS_COSINE && metric != CRS_IP) return fail(CRS_EINVAL, "metric must be COSINE or IP");
+    // int8 / 1-bit codes are defined on unit-norm rows (one global scale, sign bits): un-normalised
+    // inner-product rows would saturate at +-127 and rank wrongly
+    if (metric == CRS_IP && (store == CRS_I8 || store == CRS_B1))
+        return fail(CRS_EINVAL, "inner-product space needs a float store (F16 or BF16): I8 / B1 codes are defined on unit rows");
     const int dp = padded_dim_for(dim, store);
     if (dp < 0) return fail(CRS_EINVAL, "dim too large for this store dtype");
     int ndev = 0;
@@ -234,9 +267,10 @@ int crs_index_destroy(crs_index* ix) {
         if (ix->codes) cudaFree(ix->codes);
         if (ix->n_flagged) cudaFree(ix->n_flagged);
         for (auto& p : ix->evs) { if (p[0]) cudaEventDestroy(p[0]); if (p[1]) cudaEventDestroy(p[1]); }
+        if (ix->ev_switch) cudaEventDestroy(ix->ev_switch);
         ix->qsrc.release(); ix->qnorms.release(); ix->norms_tmp.release(); ix->qcodes.release();
         ix->stage_rows.release(); ix->vec_codes.release(); ix->cand.release(); ix->flags.release(); ix->counts_dev.release();
-        ix->ids_dev.release(); ix->scores_dev.release(); ix->allow_dev.release(); ix->tauq.release();
+        ix->ids_dev.release(); ix->scores_dev.release(); ix->allow_dev.release(); ix->floors.release();
     }
     delete ix;
     return CRS_OK;
@@ -245,7 +279,22 @@ int crs_index_destroy(crs_index* ix) {
 int crs_index_set_stream(crs_index* ix, void* cuda_stream) {
     if (!ix) return fail(CRS_EINVAL, "index is NULL");
     std::lock_guard<std::mutex> lk(ix->mu);
-    ix->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    cudaStream_t ns = reinterpret_cast<cudaStream_t>(cuda_stream);
+    if (ns != ix->stream) {
+        // the per-index scratch (candidate lists, encoded queries, flags) is shared by consecutive calls:
+        // work enqueued on the new stream must not start before what the old stream still has to do
+        DeviceGuard g(ix->device);
+        cudaStreamCaptureStatus cs_old = cudaStreamCaptureStatusNone, cs_new = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(ix->stream, &cs_old);
+        cudaStreamIsCapturing(ns, &cs_new);
+        cudaGetLastError();
+        if (cs_old == cudaStreamCaptureStatusNone && cs_new == cudaStreamCaptureStatusNone) {
+            if (!ix->ev_switch) CRS_CUDA(cudaEventCreateWithFlags(&ix->ev_switch, cudaEventDisableTiming));
+            CRS_CUDA(cudaEventRecord(ix->ev_switch, ix->stream));
+            CRS_CUDA(cudaStreamWaitEvent(ns, ix->ev_switch, 0));
+        }
+        ix->stream = ns;
+    }
     return CRS_OK;
 }
 
@@ -260,6 +309,8 @@ int crs_index_set_option(crs_index* ix, const char* name, int64_t value) {
     else if (!strcmp(name, "multi_scan")) ix->multi_scan = (int)value;
     else if (!strcmp(name, "short_lists")) ix->short_lists = (int)value;
     else if (!strcmp(name, "sample_rows")) ix->sample_rows = value;
+    else if (!strcmp(name, "share_floor")) ix->share_floor = (int)value;
+    else if (!strcmp(name, "gemm_warm")) ix->gemm_warm = (int)std::max<int64_t>(0, std::min<int64_t>(value, 64));
     else if (!strcmp(name, "eps_scale")) ix->eps_scale = (double)value / 1000.0;
     else if (!strcmp(name, "profiling")) {
         DeviceGuard g(ix->device);
@@ -346,7 +397,9 @@ int crs_index_last_stats(const crs_index* ix, crs_search_stats* out) {
     int32_t tot = 0;
     DeviceGuard g(ix->device);
     int32_t cnt[3] = {0, 0, 0};
-    CRS_CUDA(cudaMemcpy(cnt, ix->n_flagged, sizeof(cnt), cudaMemcpyDeviceToHost));
+    // on the index's own stream (non-blocking streams are not ordered with the legacy stream)
+    CRS_CUDA(cudaMemcpyAsync(cnt, ix->n_flagged, sizeof(cnt), cudaMemcpyDeviceToHost, ix->stream));
+    CRS_CUDA(cudaStreamSynchronize(ix->stream));
     tot = cnt[1];
     out->uncertified_total = tot;
     memcpy(&out->max_fast_error, &cnt[2], sizeof(float));
@@ -381,12 +434,25 @@ int crs_index_kernel_ms_history(crs_index* ix, float* out_ms, int max_n, int* n_
     return CRS_OK;
 }
 
+namespace {
+__global__ void bump_word_kernel(uint32_t* w) { *w += 1u; }
+}
+
+// ex / xphase: optional cross-shard exchange (crs_index_search_sharded and its split forms);
+// xphase 0 = push + wait + merge, 1 = push only (no outputs)
 static int search_impl(crs_index* ix, const void* queries, int nq, int k, float min_similarity,
-                       const uint32_t* allow_bits, uint32_t* out_ids, void* out_scores, int32_t* out_counts) {
+                       const uint32_t* allow_bits, uint32_t* out_ids, void* out_scores, int32_t* out_counts,
+                       crs_exchange* ex = nullptr, int xphase = 0) {
     if (!ix) return fail(CRS_EINVAL, "index is NULL");
     if (nq < 0 || k <= 0) return fail(CRS_EINVAL, "nq must be >= 0 and k > 0");
     if (nq == 0) return CRS_OK;
-    if (!queries || !out_ids || !out_scores || !out_counts) return fail(CRS_EINVAL, "NULL buffer");
+    const bool push_only = ex != nullptr && xphase == 1;
+    if (!queries || (!push_only && (!out_ids || !out_scores || !out_counts))) return fail(CRS_EINVAL, "NULL buffer");
+    if (ex != nullptr) {
+        if (!ex->wired) return fail(CRS_ESTATE, "exchange is not wired to its peers yet");
+        if (ex->device != ix->device) return fail(CRS_EINVAL, "exchange and index live on different devices");
+        if (nq > ex->max_nq || k > ex->max_k) return fail(CRS_EINVAL, "nq / k exceed what the exchange was created for");
+    }
     const bool is_float = ix->store == CRS_F16 || ix->store == CRS_BF16;
     const bool is_int = !is_float;
     // float stores need head-room above k for certification (finalize.cu)
@@ -406,9 +472,9 @@ static int search_impl(crs_index* ix, const void* queries, int nq, int k, float 
 
     const bool q_dev = is_device_ptr(queries);
     const bool ids_dev = is_device_ptr(out_ids), sc_dev = is_device_ptr(out_scores), cn_dev = is_device_ptr(out_counts);
-    if (!(ids_dev == sc_dev && sc_dev == cn_dev))
+    if (!push_only && !(ids_dev == sc_dev && sc_dev == cn_dev))
         return fail(CRS_EINVAL, "out_ids/out_scores/out_counts must all be host or all be device buffers");
-    const bool out_dev = ids_dev;
+    const bool out_dev = ids_dev || push_only;
     const size_t nk = (size_t)nq * k;
 
     uint32_t* d_ids = out_ids; void* d_scores = out_scores; int32_t* d_counts = out_counts;
@@ -418,12 +484,19 @@ static int search_impl(crs_index* ix, const void* queries, int nq, int k, float 
         CRS_CUDA(ix->counts_dev.ensure((size_t)nq));
         d_ids = ix->ids_dev.p; d_scores = ix->scores_dev.p; d_counts = ix->counts_dev.p;
     }
+    // with an exchange the local search writes into the exchange's staging area and the exchange kernel
+    // produces the final (global) result
+    uint32_t* f_ids = d_ids; void* f_scores = d_scores; int32_t* f_counts = d_counts;
+    if (ex != nullptr) {
+        const size_t cap = (size_t)ex->max_nq * ex->max_k;
+        d_ids = ex->local; d_scores = ex->local + cap; d_counts = reinterpret_cast<int32_t*>(ex->local + 2 * cap);
+    }
 
     bool copied = false;
     auto copy_out = [&]() -> cudaError_t {
-        cudaError_t e = cudaMemcpyAsync(out_ids, d_ids, nk * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(out_scores, d_scores, nk * 4, cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(out_counts, d_counts, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+        cudaError_t e = cudaMemcpyAsync(out_ids, f_ids, nk * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out_scores, f_scores, nk * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out_counts, f_counts, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
         return e;
     };
 
@@ -431,6 +504,11 @@ static int search_impl(crs_index* ix, const void* queries, int nq, int k, float 
         fill_pad_kernel<<<(unsigned)((std::max(nk, (size_t)nq) + 255) / 256), 256, 0, st>>>(d_ids, d_scores, d_counts, nq, k, is_int);
         CRS_CUDA(cudaGetLastError());
         ++launches;
+        if (ex != nullptr) {                      // an empty shard still takes part in the step
+            bump_word_kernel<<<1, 1, 0, st>>>(ex->ctl);
+            CRS_CUDA(cudaGetLastError());
+            ++launches;
+        }
     } else {
         // ---- queries -> canonical stored codes
         const float* qd = reinterpret_cast<const float*>(queries);
@@ -442,7 +520,8 @@ static int search_impl(crs_index* ix, const void* queries, int nq, int k, float 
         CRS_CUDA(ix->qcodes.ensure((size_t)nq * ix->row_bytes));
         CRS_CUDA(ix->qnorms.ensure((size_t)nq));
         CRS_CUDA(crs::launch_encode(st, qd, nq, ix->dim, ix->dim_padded, ix->store, ix->metric, ix->i8_scale,
-                                    ix->qcodes.p, ix->qnorms.p, ix->n_flagged /*reset "uncertified this search"*/));
+                                    ix->qcodes.p, ix->qnorms.p, ix->n_flagged /*reset "uncertified this search"*/,
+                                    ex ? ex->ctl : nullptr /*advance the exchange's step stamp*/));
         ++launches;
 
         // ---- plan: persistent grid, one candidate list per CTA
@@ -504,26 +583,39 @@ static int search_impl(crs_index* ix, const void* queries, int nq, int k, float 
                 uint32_t tau_bits;
                 if (is_float) memcpy(&tau_bits, &tau_pre, sizeof(tau_bits)); else tau_bits = (uint32_t)min_raw;
                 const int kind = ix->store == CRS_F16 ? 0 : (ix->store == CRS_BF16 ? 1 : 2);
-                // Sampled starting thresholds: with several query tiles the epilogue is the co-bottleneck and every
-                // (query, slice) list warms up over its first ~16K rows; a pass over the first `sample_rows` rows
-                // gives each query a floor that all slices of the full pass start from.  Valid while k fits in a
-                // slice list (the floor is the L-th best sampled key).
-                const uint32_t* tau_q = nullptr;
+                // Per-query floors.  The slices of a query run on different SMs with a list each; left alone every
+                // list warms up by itself.  (a) share_floor: the slices publish their lists' scores and a helper
+                // warp keeps the k-th best of the union in tau_q, re-read by every slice once per tile;
+                // (b) optional sample pass over the first `sample_rows` rows that seeds tau_q before the launch
+                // (valid while k fits in a slice list: the floor is the L-th best sampled key).
+                crs::GemmFloorArgs fl{};
+                const int L = crs::gemm_list_len(k);
                 const int64_t sample = ix->sample_rows;
-                if (sample > 0 && nq > 128 && k <= crs::gemm_list_len(k) && ix->count >= 8 * sample) {
+                const bool sampling = sample > 0 && nq > 128 && k <= L && ix->count >= 8 * sample;
+                const bool sharing = ix->share_floor != 0;
+                if (sampling || sharing) {
+                    const int slices_full = crs::gemm_n_slices(ix->count, nq, ix->num_sms, ix->gemm_cluster);
+                    const size_t nq_pad = ((size_t)nq + 127) / 128 * 128;
+                    const size_t words = nq_pad + (sharing ? nq_pad * (size_t)slices_full * L : 0);
+                    CRS_CUDA(ix->floors.ensure(words));
+                    CRS_CUDA(cudaMemsetAsync(ix->floors.p, 0, words * sizeof(uint32_t), st));
+                    fl.tau_q = ix->floors.p;
+                    fl.pub = sharing ? ix->floors.p + nq_pad : nullptr;
+                    fl.qnorms = ix->qnorms.p;
+                    fl.margin_rel = is_float ? 3.0f * fa.eps_rel * ix->row_norm_bound : 0.f;
+                    if (is_float) fa.tau_q = fl.tau_q;
+                }
+                if (sampling) {
                     int s_slices = 0;
-                    CRS_CUDA(ix->tauq.ensure((size_t)nq));
                     CRS_CUDA(crs::launch_gemm_topk(st, ix->codes, sample, (int)ix->row_bytes, kind, ix->qcodes.p, nq, k,
                                                    tau_bits, ix->cand.p, ix->num_sms, ix->gemm_cluster, &s_slices, plan.allow));
-                    CRS_CUDA(crs::launch_sample_tau(st, ix->cand.p, s_slices, crs::gemm_list_len(k), nq, is_int ? 1 : 0,
-                                                    ix->qnorms.p, 3.0f * fa.eps_rel * ix->row_norm_bound, ix->tauq.p));
+                    CRS_CUDA(crs::launch_sample_tau(st, ix->cand.p, s_slices, L, nq, is_int ? 1 : 0,
+                                                    ix->qnorms.p, fl.margin_rel, fl.tau_q));
                     launches += 2;
-                    tau_q = ix->tauq.p;
-                    if (is_float) fa.tau_q = tau_q;
                 }
                 CRS_CUDA(crs::launch_gemm_topk(st, ix->codes, ix->count, (int)ix->row_bytes, kind, ix->qcodes.p, nq, k,
-                                               tau_bits, ix->cand.p, ix->num_sms, ix->gemm_cluster, &n_slices, plan.allow, tau_q,
-                                               ix->gemm_prefetch));
+                                               tau_bits, ix->cand.p, ix->num_sms, ix->gemm_cluster, &n_slices, plan.allow,
+                                               fl.tau_q ? &fl : nullptr, ix->gemm_prefetch, ix->gemm_warm));
                 ++launches;
                 fa.n_lists = n_slices;
                 fa.list_len = crs::gemm_list_len(k);
@@ -561,7 +653,7 @@ static int search_impl(crs_index* ix, const void* queries, int nq, int k, float 
             CRS_CUDA(crs::launch_finalize(st, fa));
             ++launches;
             if (certifying) {
-                if (out_dev) {
+                if (out_dev || ex != nullptr) {
                     need_exact = true;          // cannot look at the flags without a sync: enqueue the conditional pass
                 } else {
                     int32_t nf = 0;             // results and the flag count come back in one sync
@@ -590,6 +682,22 @@ static int search_impl(crs_index* ix, const void* queries, int nq, int k, float 
         }
     }
 
+    if (ex != nullptr) {
+        // ---- exchange: push the local lists to every peer, wait for theirs, merge (one kernel)
+        crs::XchgArgs xa{};
+        for (int r = 0; r < ex->world; ++r) {
+            xa.peer_slots[r] = reinterpret_cast<uint32_t*>(ex->peers[r]);
+            xa.peer_flags[r] = reinterpret_cast<uint32_t*>(ex->peers[r]) + ex->slots_words;
+        }
+        xa.my_slots = ex->buf; xa.my_flags = ex->buf + ex->slots_words;
+        xa.step_word = ex->ctl; xa.err_word = ex->ctl + 1;
+        xa.local_ids = d_ids; xa.local_scores = reinterpret_cast<const uint32_t*>(d_scores);
+        xa.out_ids = f_ids; xa.out_scores = f_scores; xa.out_counts = f_counts;
+        xa.rank = ex->rank; xa.world = ex->world; xa.nq = nq; xa.k = k; xa.max_nq = ex->max_nq; xa.max_k = ex->max_k;
+        xa.flag_ctas = ex->flag_ctas; xa.is_int = is_int ? 1 : 0; xa.phase = push_only ? 1 : 0;
+        CRS_CUDA(crs::launch_xmerge(st, xa));
+        ++launches;
+    }
     if (!out_dev && !copied) {
         CRS_CUDA(copy_out());
         CRS_CUDA(cudaStreamSynchronize(st));
@@ -619,26 +727,22 @@ int crs_index_fetch_rows(crs_index* ix, const uint32_t* ids, int n, void* out_co
     DeviceGuard g(ix->device);
     cudaStream_t st = ix->stream;
     const bool ids_dev = is_device_ptr(ids), out_dev = is_device_ptr(out_codes);
-    uint32_t* d_ids = nullptr; uint8_t* d_out = nullptr;
+    DevTmp d_ids, d_out;
     const uint32_t* ids_p = ids; void* out_p = out_codes;
     const size_t bytes = (size_t)n * ix->row_bytes;
     if (!ids_dev) {
-        CRS_CUDA(cudaMalloc(&d_ids, (size_t)n * sizeof(uint32_t)));
-        CRS_CUDA(cudaMemcpyAsync(d_ids, ids, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        ids_p = d_ids;
+        CRS_CUDA(d_ids.alloc((size_t)n * sizeof(uint32_t)));
+        CRS_CUDA(cudaMemcpyAsync(d_ids.p, ids, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        ids_p = reinterpret_cast<const uint32_t*>(d_ids.p);
     }
     if (!out_dev) {
-        CRS_CUDA(cudaMalloc(&d_out, bytes));
-        CRS_CUDA(cudaMemcpyAsync(d_out, out_codes, bytes, cudaMemcpyHostToDevice, st));   // keep rows of other shards
-        out_p = d_out;
+        CRS_CUDA(d_out.alloc(bytes));
+        CRS_CUDA(cudaMemcpyAsync(d_out.p, out_codes, bytes, cudaMemcpyHostToDevice, st));   // keep rows of other shards
+        out_p = d_out.p;
     }
     CRS_CUDA(crs::launch_gather_rows(st, ix->codes, ix->row_bytes, ix->count, ix->row_base, ids_p, n, out_p));
-    if (!out_dev) CRS_CUDA(cudaMemcpyAsync(out_codes, d_out, bytes, cudaMemcpyDeviceToHost, st));
-    if (!ids_dev || !out_dev) {
-        CRS_CUDA(cudaStreamSynchronize(st));
-        if (d_ids) cudaFree(d_ids);
-        if (d_out) cudaFree(d_out);
-    }
+    if (!out_dev) CRS_CUDA(cudaMemcpyAsync(out_codes, d_out.p, bytes, cudaMemcpyDeviceToHost, st));
+    if (!ids_dev || !out_dev) CRS_CUDA(cudaStreamSynchronize(st));
     return CRS_OK;
 }
 
@@ -747,20 +851,15 @@ int crs_mmr(crs_index* ix, const void* vecs, const double* relevance, int nq, in
     cudaStream_t st = ix->stream;
     const size_t vbytes = (size_t)nq * m * ix->row_bytes, rbytes = (size_t)nq * m * sizeof(double);
     const size_t obytes = (size_t)nq * k_out * sizeof(int32_t);
-    void* d_v = nullptr; double* d_r = nullptr; int32_t* d_o = nullptr;
+    DevTmp d_v, d_r, d_o;
     const void* v = vecs; const double* r = relevance; int32_t* o = out_order;
-    if (!is_device_ptr(vecs)) { CRS_CUDA(cudaMalloc(&d_v, vbytes)); CRS_CUDA(cudaMemcpyAsync(d_v, vecs, vbytes, cudaMemcpyHostToDevice, st)); v = d_v; }
-    if (!is_device_ptr(relevance)) { CRS_CUDA(cudaMalloc(&d_r, rbytes)); CRS_CUDA(cudaMemcpyAsync(d_r, relevance, rbytes, cudaMemcpyHostToDevice, st)); r = d_r; }
+    if (!is_device_ptr(vecs)) { CRS_CUDA(d_v.alloc(vbytes)); CRS_CUDA(cudaMemcpyAsync(d_v.p, vecs, vbytes, cudaMemcpyHostToDevice, st)); v = d_v.p; }
+    if (!is_device_ptr(relevance)) { CRS_CUDA(d_r.alloc(rbytes)); CRS_CUDA(cudaMemcpyAsync(d_r.p, relevance, rbytes, cudaMemcpyHostToDevice, st)); r = reinterpret_cast<const double*>(d_r.p); }
     const bool o_dev = is_device_ptr(out_order);
-    if (!o_dev) { CRS_CUDA(cudaMalloc(&d_o, obytes)); o = d_o; }
+    if (!o_dev) { CRS_CUDA(d_o.alloc(obytes)); o = reinterpret_cast<int32_t*>(d_o.p); }
     CRS_CUDA(crs::launch_mmr(st, v, ix->store, ix->dim_padded, ix->dim, r, nq, m, k_out, lambda, o));
-    if (!o_dev) CRS_CUDA(cudaMemcpyAsync(out_order, d_o, obytes, cudaMemcpyDeviceToHost, st));
-    if (d_v || d_r || d_o) {
-        CRS_CUDA(cudaStreamSynchronize(st));
-        if (d_v) cudaFree(d_v);
-        if (d_r) cudaFree(d_r);
-        if (d_o) cudaFree(d_o);
-    }
+    if (!o_dev) CRS_CUDA(cudaMemcpyAsync(out_order, d_o.p, obytes, cudaMemcpyDeviceToHost, st));
+    if (d_v.p || d_r.p || d_o.p) CRS_CUDA(cudaStreamSynchronize(st));
     return CRS_OK;
 }
 
@@ -811,6 +910,159 @@ int crs_merge_topk_strided(void* cuda_stream, const uint32_t* ids, const void* s
         return fail(CRS_EINVAL, "crs_merge_topk_strided takes device buffers");
     CRS_CUDA(crs::launch_merge_topk(reinterpret_cast<cudaStream_t>(cuda_stream), ids, scores, is_int, n_lists, nq,
                                     k_in, k_out, out_ids, out_scores, out_counts, true, (size_t)list_stride));
+    return CRS_OK;
+}
+
+// ---- cross-shard exchange over peer memory ------------------------------------------------
+int crs_exchange_create(crs_exchange** out, int device, int rank, int world, int max_nq, int max_k) {
+    if (!out) return fail(CRS_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (world < 1 || world > crs::kMaxWorld || rank < 0 || rank >= world) return fail(CRS_EINVAL, "bad rank / world");
+    if (max_nq <= 0 || max_k <= 0 || max_k > crs::kMaxListLen) return fail(CRS_EINVAL, "bad max_nq / max_k");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(CRS_ECUDA, "no CUDA device"); }
+    if (device < 0 || device >= ndev) return fail(CRS_EINVAL, "device ordinal out of range");
+    DeviceGuard g(device);
+    crs_exchange* ex = new crs_exchange();
+    ex->device = device; ex->rank = rank; ex->world = world; ex->max_nq = max_nq; ex->max_k = max_k;
+    ex->flag_ctas = crs::xmerge_ctas(max_nq);
+    const size_t cap = (size_t)max_nq * max_k;
+    ex->slots_words = 2 * (size_t)world * 2 * cap;
+    ex->flags_words = 2 * (size_t)world * ex->flag_ctas;
+    const size_t buf_bytes = (ex->slots_words + ex->flags_words) * sizeof(uint32_t);
+    cudaError_t e = cudaMalloc(&ex->buf, buf_bytes);
+    if (e == cudaSuccess) e = cudaMemset(ex->buf, 0, buf_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&ex->ctl, 2 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemset(ex->ctl, 0, 2 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&ex->local, (2 * cap + max_nq) * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        if (ex->buf) cudaFree(ex->buf);
+        if (ex->ctl) cudaFree(ex->ctl);
+        if (ex->local) cudaFree(ex->local);
+        delete ex;
+        return cuda_fail(e, "crs_exchange_create");
+    }
+    ex->peers[rank] = ex->buf;
+    ex->wired = world == 1;
+    *out = ex;
+    return CRS_OK;
+}
+
+int crs_exchange_destroy(crs_exchange* ex) {
+    if (!ex) return CRS_OK;
+    {
+        DeviceGuard g(ex->device);
+        cudaDeviceSynchronize();
+        for (int r = 0; r < ex->world; ++r)
+            if (ex->ipc_opened[r] && ex->peers[r]) cudaIpcCloseMemHandle(ex->peers[r]);
+        if (ex->buf) cudaFree(ex->buf);
+        if (ex->ctl) cudaFree(ex->ctl);
+        if (ex->local) cudaFree(ex->local);
+        cudaGetLastError();
+    }
+    delete ex;
+    return CRS_OK;
+}
+
+int crs_exchange_ipc_handle(crs_exchange* ex, void* out_handle64) {
+    if (!ex || !out_handle64) return fail(CRS_EINVAL, "bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    DeviceGuard g(ex->device);
+    cudaIpcMemHandle_t h;
+    CRS_CUDA(cudaIpcGetMemHandle(&h, ex->buf));
+    memcpy(out_handle64, &h, sizeof(h));
+    return CRS_OK;
+}
+
+int crs_exchange_open_peers(crs_exchange* ex, const void* handles) {
+    if (!ex || !handles) return fail(CRS_EINVAL, "bad argument");
+    DeviceGuard g(ex->device);
+    for (int r = 0; r < ex->world; ++r) {
+        if (r == ex->rank || ex->peers[r]) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, reinterpret_cast<const uint8_t*>(handles) + (size_t)r * sizeof(h), sizeof(h));
+        void* p = nullptr;
+        CRS_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ex->peers[r] = p;
+        ex->ipc_opened[r] = true;
+    }
+    ex->wired = true;
+    return CRS_OK;
+}
+
+int crs_exchange_buffer(crs_exchange* ex, void** out_ptr) {
+    if (!ex || !out_ptr) return fail(CRS_EINVAL, "bad argument");
+    *out_ptr = ex->buf;
+    return CRS_OK;
+}
+
+int crs_exchange_set_peer_buffers(crs_exchange* ex, void* const* bufs) {
+    if (!ex || !bufs) return fail(CRS_EINVAL, "bad argument");
+    DeviceGuard g(ex->device);
+    for (int r = 0; r < ex->world; ++r) {
+        if (r == ex->rank) continue;
+        if (!bufs[r]) return fail(CRS_EINVAL, "NULL peer buffer");
+        cudaPointerAttributes a;
+        CRS_CUDA(cudaPointerGetAttributes(&a, bufs[r]));
+        if (a.type != cudaMemoryTypeDevice) return fail(CRS_EINVAL, "peer buffer is not device memory");
+        if (a.device != ex->device) {
+            int can = 0;
+            CRS_CUDA(cudaDeviceCanAccessPeer(&can, ex->device, a.device));
+            if (!can) return fail(CRS_ECUDA, "devices cannot access each other's memory (no P2P)");
+            cudaError_t e = cudaDeviceEnablePeerAccess(a.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+            cudaGetLastError();
+        }
+        ex->peers[r] = bufs[r];
+    }
+    ex->wired = true;
+    return CRS_OK;
+}
+
+int crs_exchange_status(crs_exchange* ex, void* cuda_stream, int* timed_out, uint32_t* step) {
+    if (!ex) return fail(CRS_EINVAL, "exchange is NULL");
+    DeviceGuard g(ex->device);
+    uint32_t w[2] = {0, 0};
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+    CRS_CUDA(cudaMemcpyAsync(w, ex->ctl, sizeof(w), cudaMemcpyDeviceToHost, st));
+    CRS_CUDA(cudaStreamSynchronize(st));
+    if (step) *step = w[0];
+    if (timed_out) *timed_out = (int)w[1];
+    return CRS_OK;
+}
+
+int crs_index_search_sharded(crs_index* ix, crs_exchange* ex, const void* queries, int nq, int k, float min_similarity,
+                             uint32_t* out_ids, void* out_scores, int32_t* out_counts) {
+    if (!ex) return fail(CRS_EINVAL, "exchange is NULL");
+    return search_impl(ix, queries, nq, k, min_similarity, nullptr, out_ids, out_scores, out_counts, ex, 0);
+}
+
+int crs_index_search_push(crs_index* ix, crs_exchange* ex, const void* queries, int nq, int k, float min_similarity) {
+    if (!ex) return fail(CRS_EINVAL, "exchange is NULL");
+    return search_impl(ix, queries, nq, k, min_similarity, nullptr, nullptr, nullptr, nullptr, ex, 1);
+}
+
+int crs_exchange_merge(crs_exchange* ex, void* cuda_stream, int nq, int k, int is_int,
+                       uint32_t* out_ids, void* out_scores, int32_t* out_counts) {
+    if (!ex) return fail(CRS_EINVAL, "exchange is NULL");
+    if (!ex->wired) return fail(CRS_ESTATE, "exchange is not wired to its peers yet");
+    if (nq < 0 || k <= 0 || nq > ex->max_nq || k > ex->max_k) return fail(CRS_EINVAL, "bad sizes");
+    if (nq == 0) return CRS_OK;
+    if (!is_device_ptr(out_ids) || !is_device_ptr(out_scores) || !is_device_ptr(out_counts))
+        return fail(CRS_EINVAL, "crs_exchange_merge takes device buffers");
+    DeviceGuard g(ex->device);
+    crs::XchgArgs xa{};
+    for (int r = 0; r < ex->world; ++r) {
+        xa.peer_slots[r] = reinterpret_cast<uint32_t*>(ex->peers[r]);
+        xa.peer_flags[r] = reinterpret_cast<uint32_t*>(ex->peers[r]) + ex->slots_words;
+    }
+    xa.my_slots = ex->buf; xa.my_flags = ex->buf + ex->slots_words;
+    xa.step_word = ex->ctl; xa.err_word = ex->ctl + 1;
+    xa.out_ids = out_ids; xa.out_scores = out_scores; xa.out_counts = out_counts;
+    xa.rank = ex->rank; xa.world = ex->world; xa.nq = nq; xa.k = k; xa.max_nq = ex->max_nq; xa.max_k = ex->max_k;
+    xa.flag_ctas = ex->flag_ctas; xa.is_int = is_int ? 1 : 0; xa.phase = 2;
+    CRS_CUDA(crs::launch_xmerge(reinterpret_cast<cudaStream_t>(cuda_stream), xa));
     return CRS_OK;
 }
 

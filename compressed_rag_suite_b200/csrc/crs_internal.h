@@ -19,7 +19,8 @@ struct ScanPlan {
 //   norms_out (optional, [n]): fp32 upper bound of the Euclidean norm of each STORED row.
 cudaError_t launch_encode(cudaStream_t st, const float* src, int64_t n, int dim, int dim_padded,
                           crs_dtype store, crs_metric metric, float i8_scale, void* dst, float* norms_out,
-                          int32_t* zero_word = nullptr /*optional device word the kernel sets to 0 (saves a memset node)*/);
+                          int32_t* zero_word = nullptr /*optional device word the kernel sets to 0 (saves a memset node)*/,
+                          uint32_t* inc_word = nullptr /*optional device word the kernel increments (exchange step stamp)*/);
 
 // K1: fp16 / bf16 stream scan of `n` stored rows against ONE stored query; writes one
 // sorted candidate list of M keys per CTA: cand[cta * M + i].
@@ -65,7 +66,8 @@ struct FinalizeArgs {
     int32_t* out_counts;       // [nq]
     int32_t* flags;            // [nq] 1 = not certified (mode 0 writes, only_flagged reads)
     int32_t* n_flagged;        // device counter of uncertified queries (statistics)
-    const uint32_t* tau_q;     // mode 0, optional: per-query fast-score floor the fast pass started from (a cut)
+    const uint32_t* tau_q;     // mode 0, optional: per-query fast-score floor (ORDERABLE f32, 0 = none) the fast pass
+                               // applied: everything below it was dropped, so it counts as a cut
     int is_int;                // raw scores are int32
     int stage_rows;            // set by launch_finalize: candidate rows are staged in shared memory before rescoring
 };
@@ -92,13 +94,26 @@ cudaError_t launch_score_rows(cudaStream_t st, const void* codes, int64_t n_rows
 // tau_pre_bits: threshold as float bits (kind 0/1) or int32 bits (kind 2).
 bool gemm_supported(int row_bytes, int k);
 int gemm_list_len(int k);
+int gemm_n_slices(int64_t n, int nq, int num_sms, int cluster);     // lists per query the launch will write
+// Per-query floors of the contraction.  tau_q: [nq] ORDERABLE 32-bit scores (orderable_f32 / orderable_i32,
+// 0 = none), read when a slice starts and — when `pub` is given — raised while the launch runs: the slices
+// of a query publish their lists' scores into pub ([nq][n_slices][gemm_list_len(k)] uint32, zeroed by the
+// caller) and a helper warp stores the k-th best score of their union (float stores: minus
+// margin_rel * |q|) back into tau_q.  After the launch tau_q[q] bounds every floor query q used.
+struct GemmFloorArgs {
+    uint32_t* tau_q;
+    uint32_t* pub;
+    const float* qnorms;
+    float margin_rel;
+};
 cudaError_t launch_gemm_topk(cudaStream_t st, const void* codes, int64_t n, int row_bytes, int kind,
                              const void* qcodes, int nq, int k, uint32_t tau_pre_bits, uint64_t* cand, int num_sms,
                              int cluster /*0 = auto, else 1|2|4 query tiles per multicast cluster*/, int* n_slices_out,
                              const uint32_t* allow /*optional row bitmap, applied to epilogue hits*/,
-                             const uint32_t* tau_q = nullptr /*optional [nq] per-query starting thresholds (score bits)*/,
-                             int prefetch_tiles = 0 /*corpus tiles the producer prefetches into L2 ahead of its ring*/);
-// per-query starting thresholds from the lists of a sample pass (L-th best key minus margin_rel * |q|)
+                             const GemmFloorArgs* floors = nullptr,
+                             int prefetch_tiles = 0 /*corpus tiles the producer prefetches into L2 ahead of its ring*/,
+                             int warm_tiles = 0 /*first tiles of every slice that only seed the floor and are redone last*/);
+// per-query floors (orderable) from the lists of a sample pass (L-th best key minus margin_rel * |q|)
 cudaError_t launch_sample_tau(cudaStream_t st, const uint64_t* cand, int n_lists, int list_len, int nq, int is_int,
                               const float* qnorms, float margin_rel, uint32_t* tau_q);
 
@@ -107,6 +122,26 @@ cudaError_t launch_merge_topk(cudaStream_t st, const uint32_t* ids, const void* 
                               int n_lists, int nq, int k_in, int k_out,
                               uint32_t* out_ids, void* out_scores, int32_t* out_counts, bool sorted_input = true,
                               size_t list_stride = 0 /*elements between consecutive lists' [nq,k_in] blocks; 0 = nq*k_in*/);
+
+// K7x: exchange + merge over NVLink peer memory (exchange.cu).  Receive buffer of a rank:
+//   slots [2 parities][world][2 blocks: ids, raw-score bits][max_nq * max_k] uint32
+//   flags [2 parities][world][flag_ctas] uint32 step stamps
+constexpr int kMaxWorld = 16;
+struct XchgArgs {
+    uint32_t* peer_slots[kMaxWorld];   // every rank's slots base (own rank included), peer-mapped
+    uint32_t* peer_flags[kMaxWorld];
+    const uint32_t* my_slots;
+    const uint32_t* my_flags;
+    const uint32_t* step_word;         // device word holding the current step stamp (advanced by the search's first kernel)
+    uint32_t* err_word;                // set to 1 when a wait times out
+    const uint32_t* local_ids;         // this rank's [nq, k] result of the local search
+    const uint32_t* local_scores;
+    uint32_t* out_ids; void* out_scores; int32_t* out_counts;
+    int rank, world, nq, k, max_nq, max_k, flag_ctas, is_int;
+    int phase;                         // 0 push + wait + merge, 1 push only, 2 wait + merge only
+};
+int xmerge_ctas(int nq);
+cudaError_t launch_xmerge(cudaStream_t st, const XchgArgs& a);
 
 // K6: greedy MMR over m candidate vectors per query.  `fused` (optional): take the search output instead of
 // a relevance array and emit the selected hits (ids / similarity / reference score) directly.

@@ -180,8 +180,8 @@ finalize_kernel(FinalizeArgs a) {
         for (int w = 0; w < kFinalizeWarps; ++w) last_fast = u64max(last_fast, cut_stage[w]);
         // the fast pass may have started from a sampled per-query floor: everything below it was dropped too
         if (a.tau_q != nullptr) {
-            const float t0 = __uint_as_float(a.tau_q[q]);
-            if (t0 > -INFINITY) last_fast = u64max(last_fast, make_key(orderable_f32(t0), 0u));
+            const uint32_t o = a.tau_q[q];
+            if (o != 0u) last_fast = u64max(last_fast, make_key(o, 0u));
         }
         bool certified = true;
         if (last_fast != 0ull) {

@@ -21,6 +21,15 @@
 //           query's 256 scores in 32-column slabs (tcgen05.ld.32x32b.x32), tests the slab
 //           maximum against its running threshold (the L-th best so far), and only on a
 //           hit walks the slab and inserts into a sorted register list of L keys.
+//   warps 6-7  floor sharing: the slices of a query tile run on different SMs and each keeps its own
+//           list, so without help every (query, slice) list warms up on its own (16 ln(n/16) inserts
+//           each, ~13x what one list over the whole shard would need).  Epilogue threads publish
+//           the scores of their list after a tile that changed it (pub[q][slice][0..L), 32-bit
+//           orderable scores, each slot monotone over time); this warp keeps merging the published
+//           lists of the queries assigned to its CTA and stores the k-th best score of the union as
+//           the query's floor (tau_q), which every slice re-reads once per tile.  A floor is valid
+//           whenever k published scores reach it — k distinct rows score at least that — whatever
+//           mix of old and new slot values a racing reader sees.
 // At the end every thread writes its sorted list: cand[q][slice][0..L) (stride M = 32).
 // finalize.cu merges the slices' lists, rescores the candidates exactly in fp64,
 // certifies the top-k and falls back to the exhaustive fp64 pass when it cannot.
@@ -34,9 +43,16 @@ namespace crs {
 #ifdef CRS_GEMM_PROFILE
 // dev instrumentation: cycles the MMA issuer spends waiting for operands / for a drained accumulator
 __device__ unsigned long long g_gemm_prof[8];
+// progress curve: [j] = sum over issuers of the cycles since CTA start at which tile 2^(j-1) (j = 0: tile 0) was begun;
+// [15] = at the end of the last tile
+__device__ unsigned long long g_gemm_tl[16];
+// floor-sharing helper: [0] rounds, [1] cycles spent in rounds, [2] helpers, [3] cycles (since CTA start) at which the
+// first floor was stored, [4] helpers that stored one; epilogue (warp 2, lane 0): [5] candidates inserted in the real
+// list, [6] slabs that took the insert path, [7] inserts during the warm-up tiles
+__device__ unsigned long long g_gemm_hp[8];
 #endif
 
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 256;      // TMA warp, MMA warp, 4 epilogue warps, 2 floor-sharing warps
 constexpr int kTileQ = 128;        // UMMA M
 constexpr int kTileC = 256;        // UMMA N (corpus rows per tile)
 constexpr int kChunkK = 64;        // fp16 elements per 128-byte swizzle row
@@ -169,15 +185,35 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
            (2ull << 61);
 }
 
-// sorted (descending) register list of L keys; insert keeps the L largest
+// One thread's candidate list: L entries sorted by (score descending, row ascending), kept as two 32-bit
+// register arrays (orderable score, 0xFFFFFFFF - row); ord == 0 marks an empty slot.
+//
+// Insert of an entry that beats the last one: its position is the number of entries that sort before it.
+// All L position tests are independent and every slot then takes one of {itself, its left neighbour, x}:
+// two dependent steps instead of an L-step compare-exchange chain (the epilogue has one warp per scheduler
+// and nothing to hide a dependent chain behind).
 template <int L>
-__device__ __forceinline__ void list_insert(uint64_t (&a)[L], uint64_t x) {
+__device__ __forceinline__ void list_insert(uint32_t (&ord)[L], uint32_t (&nid)[L], uint32_t x_ord, uint32_t x_nid) {
+    bool keep[L];
 #pragma unroll
-    for (int i = 0; i < L; ++i) {
-        const uint64_t hi = u64max(a[i], x);
-        x = u64min(a[i], x);
-        a[i] = hi;
+    for (int i = 0; i < L; ++i) keep[i] = ord[i] > x_ord || (ord[i] == x_ord && nid[i] > x_nid);
+#pragma unroll
+    for (int i = L - 1; i >= 1; --i) {
+        ord[i] = keep[i] ? ord[i] : (keep[i - 1] ? x_ord : ord[i - 1]);
+        nid[i] = keep[i] ? nid[i] : (keep[i - 1] ? x_nid : nid[i - 1]);
     }
+    ord[0] = keep[0] ? ord[0] : x_ord;
+    nid[0] = keep[0] ? nid[0] : x_nid;
+}
+// the same for a list of scores only (warm-up: group maxima)
+template <int L>
+__device__ __forceinline__ void scores_insert(uint32_t (&ord)[L], uint32_t x_ord) {
+    bool keep[L];
+#pragma unroll
+    for (int i = 0; i < L; ++i) keep[i] = ord[i] >= x_ord;
+#pragma unroll
+    for (int i = L - 1; i >= 1; --i) ord[i] = keep[i] ? ord[i] : (keep[i - 1] ? x_ord : ord[i - 1]);
+    ord[0] = keep[0] ? ord[0] : x_ord;
 }
 
 // One thread's 32 scores (consecutive corpus rows row0..row0+31 of its query).  Fast path:
@@ -202,10 +238,8 @@ __device__ __forceinline__ typename ScoreT<INT>::type from_ord(uint32_t o) {
 template <typename T> __device__ __forceinline__ T smax(T a, T b) { return a > b ? a : b; }
 template <> __device__ __forceinline__ float smax<float>(float a, float b) { return fmaxf(a, b); }
 
-template <int L, bool INT>
-__device__ __forceinline__ void slab_scan(const uint32_t (&r)[32], int64_t row0, int64_t n_rows,
-                                          typename ScoreT<INT>::type tau_pre, typename ScoreT<INT>::type& tau,
-                                          uint64_t (&best)[L], const uint32_t* __restrict__ allow) {
+template <bool INT>
+__device__ __forceinline__ typename ScoreT<INT>::type slab_max(const uint32_t (&r)[32]) {
     using T = typename ScoreT<INT>::type;
     // maximum of the 32 scores as a tree of 3-input max (FMNMX3 / VIMNMX3 on sm_100): 16 instructions
     T m[11];
@@ -218,8 +252,34 @@ __device__ __forceinline__ void slab_scan(const uint32_t (&r)[32], int64_t row0,
     m[6] = smax<T>(smax<T>(m[6], m[7]), m[8]);
     m[9] = smax<T>(m[9], m[10]);
     m[0] = smax<T>(smax<T>(m[0], m[3]), m[6]);
-    m[0] = smax<T>(m[0], m[9]);
-    if (m[0] >= tau) {
+    return smax<T>(m[0], m[9]);
+}
+
+// Warm-up tiles (see the kernel): the maxima of the slab's G-element groups go into a sorted list of L scores.
+// Each entry is the score of a different row, so the list's last entry — once the list is full — is a
+// floor that at least L rows of this slice reach.
+template <int L, bool INT, int G>
+__device__ __forceinline__ void slab_warm(const uint32_t (&r)[32], uint32_t (&top)[L], bool live, bool& dirty) {
+    using T = typename ScoreT<INT>::type;
+#pragma unroll
+    for (int g = 0; g < 32 / G; ++g) {
+        T m = score_of<INT>(r[g * G]);
+#pragma unroll
+        for (int i = 1; i < G; ++i) m = smax<T>(m, score_of<INT>(r[g * G + i]));
+        const uint32_t o = ord_of<INT>(m);
+        if (live && o > top[L - 1]) {
+            scores_insert<L>(top, o);
+            dirty = true;
+        }
+    }
+}
+
+template <int L, bool INT>
+__device__ __forceinline__ void slab_scan(const uint32_t (&r)[32], int64_t row0, int64_t n_rows,
+                                          typename ScoreT<INT>::type& tau, uint32_t (&best_ord)[L], uint32_t (&best_nid)[L],
+                                          const uint32_t* __restrict__ allow, bool& dirty) {
+    using T = typename ScoreT<INT>::type;
+    if (slab_max<INT>(r) >= tau) {
         unsigned mask = 0;
         T tmp[32];                           // dynamically indexed -> local memory, touched on this path only
 #pragma unroll
@@ -228,21 +288,121 @@ __device__ __forceinline__ void slab_scan(const uint32_t (&r)[32], int64_t row0,
             tmp[i] = v;
             mask |= (v >= tau) ? (1u << i) : 0u;
         }
-        while (mask) {
-            const int i = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const T v = tmp[i];
+        // walk this thread's own hits; the next hit's score is fetched (local memory) while the current one is inserted
+        int i = __ffs(mask) - 1;
+        mask &= mask - 1;
+        T v = tmp[i & 31];
+        while (i >= 0) {
+            int i_next = -1;
+            T v_next = v;
+            if (mask) {
+                i_next = __ffs(mask) - 1;
+                mask &= mask - 1;
+                v_next = tmp[i_next];
+            }
             const int64_t row = row0 + i;
             // row bitmap of a where / where_document filter: looked up for hits only
             if (v >= tau && row < n_rows && (allow == nullptr || ((allow[row >> 5] >> (row & 31)) & 1u))) {
-                const uint64_t key = make_key(ord_of<INT>(v), (uint32_t)row);
-                if (key > best[L - 1]) {
-                    list_insert<L>(best, key);
-                    if (best[L - 1] != 0ull) tau = smax<T>(tau_pre, from_ord<INT>(key_ord(best[L - 1])));
+                const uint32_t o = ord_of<INT>(v);
+                const uint32_t nr = 0xFFFFFFFFu - (uint32_t)row;
+                if (o > best_ord[L - 1] || (o == best_ord[L - 1] && nr > best_nid[L - 1])) {
+                    list_insert<L>(best_ord, best_nid, o, nr);
+                    dirty = true;
+                    if (best_ord[L - 1] != 0u) tau = smax<T>(tau, from_ord<INT>(best_ord[L - 1]));
                 }
             }
+            i = i_next;
+            v = v_next;
         }
     }
+}
+
+// Per-query floors (see the header comment).  tau_q holds ORDERABLE 32-bit scores (0 = none yet).
+struct GemmFloor {
+    uint32_t* tau_q;        // [nq] in/out; NULL = no floors at all
+    uint32_t* pub;          // [nq][n_slices][L] published list scores; NULL = tau_q is only read once (sample pass result)
+    const float* qnorms;    // [nq] (float stores: the floor is lowered by margin_rel * |q|)
+    float margin_rel;
+    int k;                  // rank of the union that makes the floor
+};
+
+__device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// One query's floor: k-th best of the union of its slices' published lists (a warp; LPL = 1 for k <= 32).
+// A racing reader may see a list half-updated (unsorted): the merge network then still passes on distinct
+// slots of the union — every step is a compare-exchange or a pick-one-of-two — just not necessarily the
+// largest ones, and the final sort makes position k-1 the k-th largest of those: a valid, if weaker, floor.
+// Returns 0 (no floor) when told to stop early.
+template <int LPL>
+__device__ __noinline__ uint32_t union_kth_ord(const uint32_t* __restrict__ pubq, int n_slices, int list_len, int k, int lane,
+                                                  volatile int* done) {
+    uint64_t e[LPL];
+#pragma unroll
+    for (int s = 0; s < LPL; ++s) e[s] = 0ull;
+    for (int sl = 0; sl < n_slices; ++sl) {
+        if (*done >= 4) return 0u;                          // the epilogue has finished: nobody needs the floor any more
+        uint64_t b[LPL];
+#pragma unroll
+        for (int s = 0; s < LPL; ++s) {
+            const int i = lane * LPL + s;
+            const uint32_t o = (i < list_len) ? ld_cg_u32(pubq + (size_t)sl * list_len + i) : 0u;
+            b[s] = (uint64_t)o << 32;
+        }
+        if (__shfl_sync(CRS_FULL_MASK, b[0], 0) == 0ull) continue;     // nothing published by this slice yet
+        warp_merge_desc<LPL>(e, b, lane);
+    }
+    warp_sort_desc<LPL>(e, lane);
+    const int kk = k - 1;
+    uint64_t kth = 0ull;
+#pragma unroll
+    for (int s = 0; s < LPL; ++s) {
+        const uint64_t v = shfl_u64(e[s], kk / LPL);
+        if (s == kk % LPL) kth = v;
+    }
+    return (uint32_t)(kth >> 32);
+}
+
+// The common case (k <= 32): the query's published scores are one contiguous array of n_slices * L words,
+// fetched in 32-word chunks (two lists of 16 or one of 32).  A refresh is latency-bound — one warp, and every
+// step of a bitonic network waits for a shuffle — so the work is arranged for instruction-level parallelism:
+// 8 chunks are fetched with independent loads, sorted side by side and tree-merged (3 levels) before they
+// meet the running top-32.  For L = 16 the second list of a chunk is read back to front, which makes the chunk
+// a bitonic sequence that one 5-step merge sorts.  Values below the previous k-th best cannot move the k-th
+// best any more and are dropped on load.  A list caught between two slot updates may be unsorted: the
+// networks then still pass on distinct slots, and the final sort makes position k-1 a valid floor.
+template <int L>
+__device__ __noinline__ uint32_t union_kth_small(const uint32_t* __restrict__ pubq, int n_words, int k, int lane,
+                                                 volatile int* done, uint32_t prev_kth) {
+    constexpr int G = 8;
+    const int n_chunks = (n_words + 31) / 32;
+    const int off = (L == 16 && lane >= 16) ? 47 - lane : lane;        // second list of a chunk: reversed
+    uint64_t e[1] = {0ull};
+    for (int c0 = 0; c0 < n_chunks; c0 += G) {
+        if (*done >= 4) return 0u;
+        uint64_t b[G][1];
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            const int w = (c0 + j) * 32 + off;
+            const uint32_t v = (w < n_words) ? ld_cg_u32(pubq + w) : 0u;
+            b[j][0] = (uint64_t)(v >= prev_kth ? v : 0u) << 32;
+        }
+        if constexpr (L == 16) {
+#pragma unroll
+            for (int j = 0; j < G; ++j) BitonicInner<1, 64, 16>::run(b[j], lane);
+        }
+#pragma unroll
+        for (int stride = 1; stride < G; stride *= 2) {
+#pragma unroll
+            for (int i = 0; i + stride < G; i += 2 * stride) warp_merge_desc<1>(b[i], b[i + stride], lane);
+        }
+        warp_merge_desc<1>(e, b[0], lane);
+    }
+    warp_sort_desc<1>(e, lane);
+    return (uint32_t)(shfl_u64(e[0], k - 1) >> 32);
 }
 
 template <int KCH, int L, int CS, bool INT, bool PAIR>
@@ -250,7 +410,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
                  int64_t n_rows, int n_qtiles, int n_slices, uint32_t idesc, uint32_t tau_pre_bits,
                  uint64_t* __restrict__ cand, int nq, int list_stride, const uint32_t* __restrict__ allow,
-                 const uint32_t* __restrict__ tau_q, int prefetch_tiles) {
+                 GemmFloor fl, int prefetch_tiles, int warm_tiles) {
     static_assert(!PAIR || CS == 2, "the CTA-pair MMA needs clusters of exactly two CTAs");
     // pair mode: a stage holds this CTA's half (128 rows) of a corpus chunk -> twice the stages in the same smem
     constexpr int STAGES = PAIR ? 2 * kStages : kStages;
@@ -258,12 +418,16 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[2 * kStages], empty_bar[2 * kStages], a_bar, tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_slot;
+    __shared__ int epi_done;                                  // epilogue warps that have finished their slice
 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;                                   // KCH x 16 KB
     uint8_t* smem_b = smem + KCH * kAChunkBytes;              // STAGES x BSTAGE (128 KB)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef CRS_GEMM_PROFILE
+    const long long t_cta = clock64();
+#endif
     // a cluster = CS query tiles working on the same corpus slice; its CTAs split every corpus
     // chunk CS ways and multicast the pieces to each other (one L2 read feeds CS SMs)
     const int crank = (CS > 1) ? (int)cluster_ctarank() : 0;
@@ -276,8 +440,17 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     const int64_t tile_lo = tiles_total * slice / n_slices;
     const int64_t tile_hi = tiles_total * (slice + 1) / n_slices;
     const int n_tiles = (int)(tile_hi - tile_lo);
+    // Deferred warm-up.  A slice's list starts empty, and until its floor is tight nearly every score is a
+    // candidate: inserting them kept the epilogue far behind the tensor core for the first ~30 tiles of every
+    // slice (measured: ~200 K cycles per launch).  Instead the first n_warm tiles are only LOOKED at — the
+    // maxima of small groups of scores go into a score-only list, published to the floor sharing like a real
+    // list — and are computed a second time at the END of the slice, when the floor is tight and almost
+    // nothing in them is a candidate.  Costs n_warm extra tiles of MMA per slice.
+    const int n_warm = (allow == nullptr && warm_tiles > 0 && n_tiles >= 4 * warm_tiles) ? warm_tiles : 0;
+    const int n_iter = n_tiles + n_warm;                      // iteration it works on tile (it < n_tiles ? it : it - n_tiles)
 
     if (threadIdx.x == 0) {
+        epi_done = 0;
         // pair mode: one commit (multicast to both CTAs) frees a stage; the accumulator-drained barrier of
         // rank 0 collects the 4 epilogue warps of BOTH CTAs
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], PAIR ? 1 : CS); }
@@ -302,7 +475,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 for (int kc = 0; kc < KCH; ++kc)
                     tma_load_2d_pair(smem_a + kc * kAChunkBytes, &map_q, kc * (INT ? 128 : kChunkK), qtile * kTileQ, a_bar0);
                 int stage = 0; uint32_t phase = 0;
-                for (int t = 0; t < n_tiles; ++t) {
+                for (int it = 0; it < n_iter; ++it) {
+                    const int t = it < n_tiles ? it : it - n_tiles;
                     const int row0 = (int)((tile_lo + t) * kTileC) + crank * (kTileC / 2);
                     if (prefetch_tiles > 0 && t + prefetch_tiles < n_tiles)
                         for (int kc = 0; kc < KCH; ++kc)
@@ -320,7 +494,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             for (int kc = 0; kc < KCH; ++kc)
                 tma_load_2d(smem_a + kc * kAChunkBytes, &map_q, kc * (INT ? 128 : kChunkK), qtile * kTileQ, &a_bar);
             int stage = 0; uint32_t phase = 0;
-            for (int t = 0; t < n_tiles; ++t) {
+            for (int it = 0; it < n_iter; ++it) {
+                const int t = it < n_tiles ? it : it - n_tiles;
                 const int row0 = (int)((tile_lo + t) * kTileC);
                 if (prefetch_tiles > 0 && t + prefetch_tiles < n_tiles) {   // this CTA's piece of a tile ahead -> L2
                     const int prow = (int)((tile_lo + t + prefetch_tiles) * kTileC) + crank * (kTileC / CS);
@@ -350,11 +525,15 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             long long w_full = 0, w_empty = 0, t_begin = clock64();
 #endif
             int stage = 0; uint32_t phase = 0;
-            for (int t = 0; t < n_tiles; ++t) {
+            for (int t = 0; t < n_iter; ++t) {
                 const int buf = t & 1;
                 const uint32_t tphase = (t >> 1) & 1;
 #ifdef CRS_GEMM_PROFILE
                 long long c0 = clock64();
+                if ((t & (t - 1)) == 0) {                   // t = 0, 1, 2, 4, 8, ...
+                    const int j = t == 0 ? 0 : 32 - __clz(t);
+                    if (j < 15) atomicAdd(&g_gemm_tl[j], (unsigned long long)(c0 - t_cta));
+                }
 #endif
                 mbar_wait(&tempty_bar[buf], tphase ^ 1);            // epilogue has drained this accumulator
 #ifdef CRS_GEMM_PROFILE
@@ -396,6 +575,57 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             atomicAdd(&g_gemm_prof[1], (unsigned long long)w_empty);
             atomicAdd(&g_gemm_prof[2], (unsigned long long)(clock64() - t_begin));
             atomicAdd(&g_gemm_prof[3], 1ull);
+            atomicAdd(&g_gemm_prof[7], (unsigned long long)n_iter);
+            atomicAdd(&g_gemm_tl[15], (unsigned long long)(clock64() - t_cta));
+#endif
+        }
+    } else if (warp >= 6) {
+        // ------------------------------------------------------------ floor sharing (see the header comment)
+        if (fl.pub != nullptr) {
+            volatile int* done = &epi_done;
+            __shared__ uint32_t prev[8];                            // k-th best of the last refresh, per assigned query
+            if (lane < 8 && (lane & 1) == warp - 6) prev[lane] = 0u;     // this warp's queries
+            __syncwarp();
+#ifdef CRS_GEMM_PROFILE
+            long long h_rounds = 0, h_cyc = 0, h_first = 0;
+#endif
+            while (*done < 4) {
+#ifdef CRS_GEMM_PROFILE
+                const long long h0 = clock64();
+#endif
+#pragma unroll 1
+                for (int j = warp - 6; j < 8; j += 2) {             // each query of the tile belongs to one slice's CTA (and one of its two helper warps)
+                    const int i = slice + j * n_slices;
+                    const int q = qtile * kTileQ + i;
+                    if (i >= kTileQ || q >= nq || *done >= 4) break;
+                    const uint32_t* pubq = fl.pub + (size_t)q * n_slices * L;
+                    const uint32_t o = (fl.k <= 32) ? union_kth_small<L>(pubq, n_slices * L, fl.k, lane, done, prev[j])
+                                                    : union_kth_ord<4>(pubq, n_slices, L, fl.k, lane, done);
+                    if (o != 0u) {
+                        if (lane == 0) {
+                            prev[j] = o;
+                            uint32_t f = o;
+                            if constexpr (!INT) f = orderable_f32(unorderable_f32(o) - fl.margin_rel * fl.qnorms[q]);
+                            atomicMax(fl.tau_q + q, f);
+#ifdef CRS_GEMM_PROFILE
+                            if (h_first == 0) h_first = clock64() - t_cta;
+#endif
+                        }
+                        __syncwarp();
+                    }
+                }
+#ifdef CRS_GEMM_PROFILE
+                h_cyc += clock64() - h0; ++h_rounds;
+#endif
+                __nanosleep(200);
+            }
+#ifdef CRS_GEMM_PROFILE
+            if (lane == 0) {
+                atomicAdd(&g_gemm_hp[0], (unsigned long long)h_rounds);
+                atomicAdd(&g_gemm_hp[1], (unsigned long long)h_cyc);
+                atomicAdd(&g_gemm_hp[2], 1ull);
+                if (h_first) { atomicAdd(&g_gemm_hp[3], (unsigned long long)h_first); atomicAdd(&g_gemm_hp[4], 1ull); }
+            }
 #endif
         }
     } else {
@@ -403,40 +633,72 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         const int lane_grp = warp & 3;                              // TMEM lanes this warp may touch
         const int qrow = lane_grp * 32 + lane;
         const int q = qtile * kTileQ + qrow;
-        uint64_t best[L];
+        uint32_t best_ord[L], best_nid[L];
 #pragma unroll
-        for (int i = 0; i < L; ++i) best[i] = 0ull;
+        for (int i = 0; i < L; ++i) { best_ord[i] = 0u; best_nid[i] = 0u; }
         // running threshold: L-th best so far.  Padding rows of the last query tile (all-zero
         // queries, every score 0) must never enter the slow path: their threshold is +inf.
         using T = typename ScoreT<INT>::type;
         const T tau_pre = score_of<INT>(tau_pre_bits);
         T tau;
         if constexpr (INT) tau = (q < nq) ? tau_pre : INT32_MAX; else tau = (q < nq) ? tau_pre : INFINITY;
-        // optional per-query starting threshold from a sample of the shard (see sample_tau_kernel): every
-        // slice starts where a scan of the sample would have ended instead of warming its list up from nothing
-        T tau_start = tau_pre;
-        if (tau_q != nullptr && q < nq) { tau_start = smax<T>(tau_pre, score_of<INT>(tau_q[q])); tau = tau_start; }
-        for (int t = 0; t < n_tiles; ++t) {
-            const int buf = t & 1;
-            const uint32_t tphase = (t >> 1) & 1;
+        // per-query floor: from a sample pass (read once) and / or shared between the slices while they run
+        // (re-read once per tile; the load is issued here and consumed after the tile's slabs)
+        const bool floors = fl.tau_q != nullptr && q < nq;
+        const bool sharing = floors && fl.pub != nullptr;
+        if (floors) {
+            const uint32_t o = ld_cg_u32(fl.tau_q + q);
+            if (o != 0u) tau = smax<T>(tau, from_ord<INT>(o));
+        }
+        bool dirty = false;
+#ifdef CRS_GEMM_PROFILE
+        long long e_wait = 0, e_begin = clock64();
+#endif
+        for (int it = 0; it < n_iter; ++it) {
+            const int buf = it & 1;
+            const uint32_t tphase = (it >> 1) & 1;
+            const int t = it < n_tiles ? it : it - n_tiles;
+#ifdef CRS_GEMM_PROFILE
+            const long long ew0 = clock64();
+#endif
             mbar_wait(&tfull_bar[buf], tphase);
+#ifdef CRS_GEMM_PROFILE
+            e_wait += clock64() - ew0;
+#endif
             tc_fence_after();
+            uint32_t floor_ord = 0u;
+            if (sharing) floor_ord = ld_cg_u32(fl.tau_q + q);
             const int64_t row0 = (tile_lo + t) * kTileC;
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + buf * kTileC;
             // two register slabs in flight: the TMEM load of slab s+1 overlaps the scan of slab s
             uint32_t ra[32], rb[32];
             tmem_ld32(taddr, ra);
             tmem_ld_wait();
+            if (it < n_warm) {
+                // warm-up tile: group maxima only (best_ord serves as the score-only list, best_nid is unused)
 #pragma unroll 1
-            for (int slab = 0; slab < kTileC / 32; slab += 2) {
-                tmem_ld32(taddr + (slab + 1) * 32, rb);
-                slab_scan<L, INT>(ra, row0 + slab * 32, n_rows, tau_start, tau, best, allow);
-                __syncwarp();                                       // tcgen05.ld / wait are .aligned: reconverge first
-                tmem_ld_wait();
-                if (slab + 2 < kTileC / 32) tmem_ld32(taddr + (slab + 2) * 32, ra);
-                slab_scan<L, INT>(rb, row0 + (slab + 1) * 32, n_rows, tau_start, tau, best, allow);
-                __syncwarp();
-                tmem_ld_wait();
+                for (int slab = 0; slab < kTileC / 32; slab += 2) {
+                    tmem_ld32(taddr + (slab + 1) * 32, rb);
+                    slab_warm<L, INT, kTileC / L>(ra, best_ord, q < nq, dirty);
+                    __syncwarp();
+                    tmem_ld_wait();
+                    if (slab + 2 < kTileC / 32) tmem_ld32(taddr + (slab + 2) * 32, ra);
+                    slab_warm<L, INT, kTileC / L>(rb, best_ord, q < nq, dirty);
+                    __syncwarp();
+                    tmem_ld_wait();
+                }
+            } else {
+#pragma unroll 1
+                for (int slab = 0; slab < kTileC / 32; slab += 2) {
+                    tmem_ld32(taddr + (slab + 1) * 32, rb);
+                    slab_scan<L, INT>(ra, row0 + slab * 32, n_rows, tau, best_ord, best_nid, allow, dirty);
+                    __syncwarp();                                   // tcgen05.ld / wait are .aligned: reconverge first
+                    tmem_ld_wait();
+                    if (slab + 2 < kTileC / 32) tmem_ld32(taddr + (slab + 2) * 32, ra);
+                    slab_scan<L, INT>(rb, row0 + (slab + 1) * 32, n_rows, tau, best_ord, best_nid, allow, dirty);
+                    __syncwarp();
+                    tmem_ld_wait();
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -444,11 +706,38 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 if constexpr (PAIR) mbar_arrive_cluster(mapa_rank0(smem_u32(&tempty_bar[buf])));
                 else mbar_arrive(&tempty_bar[buf]);
             }
+            if (sharing) {
+                if (dirty) {
+                    // publish this list's scores: every slot only ever grows (atomic max), whichever of the two
+                    // lists — warm-up scores, then the real list — it is fed from
+                    uint32_t* dstp = fl.pub + ((size_t)q * n_slices + slice) * L;
+#pragma unroll
+                    for (int i = 0; i < L; ++i)
+                        if (best_ord[i] != 0u) atomicMax(dstp + i, best_ord[i]);
+                    dirty = false;
+                }
+                if (floor_ord != 0u) tau = smax<T>(tau, from_ord<INT>(floor_ord));
+            }
+            if (it + 1 == n_warm) {
+                // end of the warm-up: its L-th best group maximum is this slice's first floor; the real list starts empty
+                if (q < nq && best_ord[L - 1] != 0u) tau = smax<T>(tau, from_ord<INT>(best_ord[L - 1]));
+#pragma unroll
+                for (int i = 0; i < L; ++i) { best_ord[i] = 0u; best_nid[i] = 0u; }
+            }
         }
+        __syncwarp();
+        if (lane == 0) atomicAdd(&epi_done, 1);
+#ifdef CRS_GEMM_PROFILE
+        if (lane == 0 && warp == 2) {            // one epilogue warp per CTA: cycles waiting for an accumulator / in total
+            atomicAdd(&g_gemm_prof[4], (unsigned long long)e_wait);
+            atomicAdd(&g_gemm_prof[5], (unsigned long long)(clock64() - e_begin));
+            atomicAdd(&g_gemm_prof[6], 1ull);
+        }
+#endif
         if (q < nq) {
             uint64_t* dst = cand + ((size_t)q * n_slices + slice) * list_stride;
 #pragma unroll
-            for (int i = 0; i < L; ++i) dst[i] = best[i];
+            for (int i = 0; i < L; ++i) dst[i] = ((uint64_t)best_ord[i] << 32) | (uint64_t)best_nid[i];
             for (int i = L; i < list_stride; ++i) dst[i] = 0ull;
         }
     }
@@ -461,11 +750,15 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 
 #ifdef CRS_GEMM_PROFILE
 }  // namespace crs
-extern "C" __attribute__((visibility("default"))) int crs_debug_gemm_profile(unsigned long long* out8, int reset) {
-    cudaError_t e = cudaMemcpyFromSymbol(out8, crs::g_gemm_prof, sizeof(unsigned long long) * 8);
+extern "C" __attribute__((visibility("default"))) int crs_debug_gemm_profile(unsigned long long* out24 /*[32]*/, int reset) {
+    cudaError_t e = cudaMemcpyFromSymbol(out24, crs::g_gemm_prof, sizeof(unsigned long long) * 8);
+    if (e == cudaSuccess) e = cudaMemcpyFromSymbol(out24 + 8, crs::g_gemm_tl, sizeof(unsigned long long) * 16);
+    if (e == cudaSuccess) e = cudaMemcpyFromSymbol(out24 + 24, crs::g_gemm_hp, sizeof(unsigned long long) * 8);
     if (e == cudaSuccess && reset) {
-        unsigned long long z[8] = {0};
-        e = cudaMemcpyToSymbol(crs::g_gemm_prof, z, sizeof(z));
+        unsigned long long z[16] = {0};
+        e = cudaMemcpyToSymbol(crs::g_gemm_prof, z, sizeof(unsigned long long) * 8);
+        if (e == cudaSuccess) e = cudaMemcpyToSymbol(crs::g_gemm_tl, z, sizeof(z));
+        if (e == cudaSuccess) e = cudaMemcpyToSymbol(crs::g_gemm_hp, z, sizeof(unsigned long long) * 8);
     }
     return e == cudaSuccess ? 0 : 2;
 }
@@ -491,15 +784,10 @@ sample_tau_kernel(const uint64_t* __restrict__ cand, int n_lists, int list_len, 
         warp_merge_desc<1>(e, b, lane);
     }
     const uint64_t lth = shfl_u64(e[0], list_len - 1);
-    if (lane == 0) {
-        uint32_t bits;
-        if (is_int) {
-            bits = (lth != 0ull) ? (uint32_t)unorderable_i32(key_ord(lth)) : (uint32_t)INT32_MIN;
-        } else {
-            const float t = (lth != 0ull) ? unorderable_f32(key_ord(lth)) - margin_rel * qnorms[q] : -INFINITY;
-            bits = __float_as_uint(t);
-        }
-        tau_q[q] = bits;
+    if (lane == 0) {                                   // orderable score, 0 = no floor
+        uint32_t o = 0u;
+        if (lth != 0ull) o = is_int ? key_ord(lth) : orderable_f32(unorderable_f32(key_ord(lth)) - margin_rel * qnorms[q]);
+        tau_q[q] = o;
     }
 }
 
@@ -546,7 +834,7 @@ static bool make_map(CUtensorMap* map, const void* base, int64_t rows, int row_b
 template <int KCH, int L, int CS, bool INT, bool PAIR>
 static cudaError_t launch_kch(cudaStream_t st, const CUtensorMap& mq, const CUtensorMap& mc, int64_t n, int n_qtiles,
                               int n_slices, uint32_t idesc, uint32_t tau_pre, uint64_t* cand, int nq, int list_stride,
-                              const uint32_t* allow, const uint32_t* tau_q, int prefetch_tiles) {
+                              const uint32_t* allow, const GemmFloor& fl, int prefetch_tiles, int warm_tiles) {
     const size_t smem = (size_t)KCH * kAChunkBytes + (size_t)kStages * kBStageBytes + 1024;
     auto kern = gemm_topk_kernel<KCH, L, CS, INT, PAIR>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -563,20 +851,20 @@ static cudaError_t launch_kch(cudaStream_t st, const CUtensorMap& mq, const CUte
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, list_stride, allow, tau_q, prefetch_tiles);
+    return cudaLaunchKernelEx(&cfg, kern, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, list_stride, allow, fl, prefetch_tiles, warm_tiles);
 }
 
 template <int KCH, int L, bool INT>
 static cudaError_t launch_cs(int cs, cudaStream_t st, const CUtensorMap& mq, const CUtensorMap& mc, int64_t n,
                              int n_qtiles, int n_slices, uint32_t idesc, uint32_t tau_pre, uint64_t* cand, int nq,
-                             const uint32_t* allow, const uint32_t* tau_q, int prefetch_tiles) {
+                             const uint32_t* allow, const GemmFloor& fl, int prefetch_tiles, int warm_tiles) {
     if (cs == 22) {     // CTA pair: M = 256 across the two SMs of a cluster
         const uint32_t idesc_pair = (idesc & ~(0x1Fu << 24)) | ((uint32_t)(2 * kTileQ >> 4) << 24);
-        return launch_kch<KCH, L, 2, INT, true>(st, mq, mc, n, n_qtiles, n_slices, idesc_pair, tau_pre, cand, nq, 32, allow, tau_q, prefetch_tiles);
+        return launch_kch<KCH, L, 2, INT, true>(st, mq, mc, n, n_qtiles, n_slices, idesc_pair, tau_pre, cand, nq, 32, allow, fl, prefetch_tiles, warm_tiles);
     }
-    if (cs == 4) return launch_kch<KCH, L, 4, INT, false>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32, allow, tau_q, prefetch_tiles);
-    if (cs == 2) return launch_kch<KCH, L, 2, INT, false>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32, allow, tau_q, prefetch_tiles);
-    return launch_kch<KCH, L, 1, INT, false>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32, allow, tau_q, prefetch_tiles);
+    if (cs == 4) return launch_kch<KCH, L, 4, INT, false>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32, allow, fl, prefetch_tiles, warm_tiles);
+    if (cs == 2) return launch_kch<KCH, L, 2, INT, false>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32, allow, fl, prefetch_tiles, warm_tiles);
+    return launch_kch<KCH, L, 1, INT, false>(st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre, cand, nq, 32, allow, fl, prefetch_tiles, warm_tiles);
 }
 
 // kind: 0 fp16, 1 bf16, 2 int8
@@ -587,11 +875,37 @@ bool gemm_supported(int row_bytes, int k) {
 
 int gemm_list_len(int k) { return k <= 10 ? 16 : 32; }
 
-cudaError_t launch_gemm_topk(cudaStream_t st, const void* codes, int64_t n, int row_bytes, int kind,
-                             const void* qcodes, int nq, int k, uint32_t tau_pre_bits, uint64_t* cand, int num_sms,
-                             int cluster, int* n_slices_out, const uint32_t* allow, const uint32_t* tau_q,
-                             int prefetch_tiles) {
-    const int kch = row_bytes / 128;
+// Clusters of `cs` CTAs (1 CTA / SM: every instantiation asks for ~225 KB of shared memory) that can be resident
+// at once on this GPU — clusters must sit inside one GPC, so this can be less than num_sms / cs.  A grid with
+// more clusters than that would run in two waves.  Asked once per cluster size (for the widest instantiation).
+static int max_resident_clusters(int cs) {
+    static int cache[5] = {0, 0, 0, 0, 0};
+    if (cs < 1 || cs > 4) return 0;
+    if (cache[cs] != 0) return cache[cs];
+    const void* kern = cs == 4 ? (const void*)gemm_topk_kernel<6, 16, 4, false, false>
+                     : cs == 2 ? (const void*)gemm_topk_kernel<6, 16, 2, false, false>
+                               : (const void*)gemm_topk_kernel<6, 16, 1, false, false>;
+    const size_t smem = (size_t)6 * kAChunkBytes + (size_t)kStages * kBStageBytes + 1024;
+    int n = 0;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(cs * 64);
+        cfg.blockDim = dim3(kGemmThreads);
+        cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) n = 0;
+    }
+    cudaGetLastError();
+    cache[cs] = n > 0 ? n : -1;
+    return cache[cs];
+}
+
+// work split of one launch: query tiles (padded to the cluster size), corpus slices, cluster size
+static void gemm_plan(int64_t n, int nq, int num_sms, int cluster, int* n_qtiles_out, int* n_slices_out, int* cs_out,
+                      bool* pair_out) {
     int n_qtiles = (nq + kTileQ - 1) / kTileQ;
     // cluster size: query tiles that share one corpus stream through TMA multicast
     const bool pair = (cluster == 22) && n_qtiles >= 2;      // option value 22: CTA-pair MMA (cta_group::2)
@@ -600,10 +914,33 @@ cudaError_t launch_gemm_topk(cudaStream_t st, const void* codes, int64_t n, int 
     while (cs > 1 && n_qtiles < cs) cs >>= 1;
     n_qtiles = (n_qtiles + cs - 1) / cs * cs;              // padded query tiles are all-zero (TMA OOB fill)
     int n_slices = num_sms / n_qtiles;
+    const int fit = max_resident_clusters(cs);             // one wave: no more clusters than can be resident together
+    if (fit > 0 && n_slices * (n_qtiles / cs) > fit) n_slices = fit / (n_qtiles / cs);
     if (n_slices < 1) n_slices = 1;
     const int64_t tiles_total = (n + kTileC - 1) / kTileC;
     if (n_slices > tiles_total) n_slices = (int)tiles_total;
+    *n_qtiles_out = n_qtiles; *n_slices_out = n_slices; *cs_out = cs; *pair_out = pair;
+}
+
+int gemm_n_slices(int64_t n, int nq, int num_sms, int cluster) {
+    int n_qtiles, n_slices, cs; bool pair;
+    gemm_plan(n, nq, num_sms, cluster, &n_qtiles, &n_slices, &cs, &pair);
+    return n_slices;
+}
+
+cudaError_t launch_gemm_topk(cudaStream_t st, const void* codes, int64_t n, int row_bytes, int kind,
+                             const void* qcodes, int nq, int k, uint32_t tau_pre_bits, uint64_t* cand, int num_sms,
+                             int cluster, int* n_slices_out, const uint32_t* allow, const GemmFloorArgs* floors,
+                             int prefetch_tiles, int warm_tiles) {
+    const int kch = row_bytes / 128;
+    int n_qtiles, n_slices, cs; bool pair;
+    gemm_plan(n, nq, num_sms, cluster, &n_qtiles, &n_slices, &cs, &pair);
     *n_slices_out = n_slices;
+    GemmFloor fl{};
+    if (floors != nullptr) {
+        fl.tau_q = floors->tau_q; fl.pub = floors->pub; fl.qnorms = floors->qnorms; fl.margin_rel = floors->margin_rel;
+    }
+    fl.k = k;
     CUtensorMap mq, mc;
     if (!make_map(&mq, qcodes, nq, row_bytes, kTileQ, kind) || !make_map(&mc, codes, n, row_bytes, kTileC / cs, kind))
         return cudaErrorInvalidValue;
@@ -617,10 +954,10 @@ cudaError_t launch_gemm_topk(cudaStream_t st, const void* codes, int64_t n, int 
 #define CRS_GEMM_CASE(KCH_)                                                                                              \
     case KCH_:                                                                                                           \
         if (kind == 2)                                                                                                   \
-            return L == 16 ? launch_cs<KCH_, 16, true>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq, allow, tau_q, prefetch_tiles)   \
-                           : launch_cs<KCH_, 32, true>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq, allow, tau_q, prefetch_tiles);  \
-        return L == 16 ? launch_cs<KCH_, 16, false>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq, allow, tau_q, prefetch_tiles)      \
-                       : launch_cs<KCH_, 32, false>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq, allow, tau_q, prefetch_tiles);
+            return L == 16 ? launch_cs<KCH_, 16, true>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq, allow, fl, prefetch_tiles, warm_tiles)   \
+                           : launch_cs<KCH_, 32, true>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq, allow, fl, prefetch_tiles, warm_tiles);  \
+        return L == 16 ? launch_cs<KCH_, 16, false>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq, allow, fl, prefetch_tiles, warm_tiles)      \
+                       : launch_cs<KCH_, 32, false>(cs, st, mq, mc, n, n_qtiles, n_slices, idesc, tau_pre_bits, cand, nq, allow, fl, prefetch_tiles, warm_tiles);
     switch (kch) {
         CRS_GEMM_CASE(1)
         CRS_GEMM_CASE(2)

@@ -20,9 +20,11 @@ constexpr int kIngestWarps = 4;
 template <int STORE>   // crs_dtype value
 __global__ void __launch_bounds__(kIngestWarps * 32)
 encode_kernel(const float* __restrict__ src, int64_t n, int dim, int dim_padded, int cosine,
-              double i8_mult, void* __restrict__ dst, float* __restrict__ norms_out, int32_t* __restrict__ zero_word) {
+              double i8_mult, void* __restrict__ dst, float* __restrict__ norms_out, int32_t* __restrict__ zero_word,
+              uint32_t* __restrict__ inc_word) {
     __shared__ float tile[kIngestWarps][32][33];
     if (zero_word != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *zero_word = 0;   // per-search counter reset rides along
+    if (inc_word != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *inc_word += 1u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row0 = ((int64_t)blockIdx.x * kIngestWarps + warp) * 32;
     if (row0 >= n) return;
@@ -97,11 +99,13 @@ constexpr int kSmallRows = 8;            // rows per CTA: 1024 queries -> 128 CT
 template <int STORE>
 __global__ void __launch_bounds__(kSmallThreads)
 encode_small_kernel(const float* __restrict__ src, int64_t n, int dim, int dim_padded, int cosine,
-                    double i8_mult, void* __restrict__ dst, float* __restrict__ norms_out, int32_t* __restrict__ zero_word) {
+                    double i8_mult, void* __restrict__ dst, float* __restrict__ norms_out, int32_t* __restrict__ zero_word,
+                    uint32_t* __restrict__ inc_word) {
     extern __shared__ float rows_sm[];                       // [kSmallRows][dim + 1]
     __shared__ double s_div[32];
     __shared__ int s_zero[32];
     if (zero_word != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *zero_word = 0;
+    if (inc_word != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *inc_word += 1u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row0 = (int64_t)blockIdx.x * kSmallRows;
     const int rows_here = (int)min((int64_t)kSmallRows, n - row0);
@@ -154,7 +158,7 @@ encode_small_kernel(const float* __restrict__ src, int64_t n, int dim, int dim_p
 
 cudaError_t launch_encode(cudaStream_t st, const float* src, int64_t n, int dim, int dim_padded,
                           crs_dtype store, crs_metric metric, float i8_scale, void* dst, float* norms_out,
-                          int32_t* zero_word) {
+                          int32_t* zero_word, uint32_t* inc_word) {
     if (n <= 0) return cudaSuccess;
     const int64_t rows_per_block = kIngestWarps * 32;
     const unsigned grid = (unsigned)((n + rows_per_block - 1) / rows_per_block);
@@ -167,7 +171,7 @@ cudaError_t launch_encode(cudaStream_t st, const float* src, int64_t n, int dim,
         do {                                                                                                     \
             cudaError_t e = cudaFuncSetAttribute(encode_small_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem); \
             if (e != cudaSuccess) return e;                                                                      \
-            encode_small_kernel<S><<<g, kSmallThreads, small_smem, st>>>(src, n, dim, dim_padded, cosine, mult, dst, norms_out, zero_word); \
+            encode_small_kernel<S><<<g, kSmallThreads, small_smem, st>>>(src, n, dim, dim_padded, cosine, mult, dst, norms_out, zero_word, inc_word); \
         } while (0)
         switch (store) {
             case CRS_F16:  CRS_ENC_SMALL(CRS_F16); break;
@@ -180,10 +184,10 @@ cudaError_t launch_encode(cudaStream_t st, const float* src, int64_t n, int dim,
         return cudaGetLastError();
     }
     switch (store) {
-        case CRS_F16:  encode_kernel<CRS_F16><<<grid, kIngestWarps * 32, 0, st>>>(src, n, dim, dim_padded, cosine, mult, dst, norms_out, zero_word); break;
-        case CRS_BF16: encode_kernel<CRS_BF16><<<grid, kIngestWarps * 32, 0, st>>>(src, n, dim, dim_padded, cosine, mult, dst, norms_out, zero_word); break;
-        case CRS_I8:   encode_kernel<CRS_I8><<<grid, kIngestWarps * 32, 0, st>>>(src, n, dim, dim_padded, cosine, mult, dst, norms_out, zero_word); break;
-        case CRS_B1:   encode_kernel<CRS_B1><<<grid, kIngestWarps * 32, 0, st>>>(src, n, dim, dim_padded, cosine, mult, dst, norms_out, zero_word); break;
+        case CRS_F16:  encode_kernel<CRS_F16><<<grid, kIngestWarps * 32, 0, st>>>(src, n, dim, dim_padded, cosine, mult, dst, norms_out, zero_word, inc_word); break;
+        case CRS_BF16: encode_kernel<CRS_BF16><<<grid, kIngestWarps * 32, 0, st>>>(src, n, dim, dim_padded, cosine, mult, dst, norms_out, zero_word, inc_word); break;
+        case CRS_I8:   encode_kernel<CRS_I8><<<grid, kIngestWarps * 32, 0, st>>>(src, n, dim, dim_padded, cosine, mult, dst, norms_out, zero_word, inc_word); break;
+        case CRS_B1:   encode_kernel<CRS_B1><<<grid, kIngestWarps * 32, 0, st>>>(src, n, dim, dim_padded, cosine, mult, dst, norms_out, zero_word, inc_word); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

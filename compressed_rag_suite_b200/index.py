@@ -171,6 +171,55 @@ class ShardIndex:
                                                         cnt.ctypes.data_as(C.c_void_p)))
         return ids, sc, cnt
 
+    # ------------------------------------------------------------------ sharded search over peer memory
+    def search_sharded(self, exchange, queries, k: int, min_similarity: float = -math.inf, out=None):
+        """Local search + exchange + merge in the library (crs_index_search_sharded): every rank gets the
+        GLOBAL top-k.  torch CUDA in -> torch CUDA out (enqueued); numpy in -> numpy out (synchronous).
+        out: optional preallocated (ids, scores, counts) of the matching kind."""
+        if _is_torch_cuda(queries):
+            import torch
+            q = queries if queries.dim() == 2 else queries[None, :]
+            if q.dtype != torch.float32 or q.shape[1] != self.dim:
+                raise ValueError(f"queries must be float32 [nq, {self.dim}]")
+            q = q.contiguous()
+            nq = q.shape[0]
+            if out is not None:
+                ids, sc, cnt = out
+            else:
+                ids = torch.empty((nq, k), dtype=torch.int32, device=q.device)
+                sc = torch.empty((nq, k), dtype=torch.int32 if self.is_int else torch.float32, device=q.device)
+                cnt = torch.empty((nq,), dtype=torch.int32, device=q.device)
+            self._use_torch_stream()
+            N.check(self._lib.crs_index_search_sharded(self._h, exchange._h, C.c_void_p(q.data_ptr()), nq, int(k),
+                                                       float(min_similarity), C.c_void_p(ids.data_ptr()),
+                                                       C.c_void_p(sc.data_ptr()), C.c_void_p(cnt.data_ptr())))
+            return ids, sc, cnt
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"queries must be float32 [nq, {self.dim}], got {q.shape}")
+        nq = q.shape[0]
+        if out is not None:
+            ids, sc, cnt = out
+        else:
+            ids = np.empty((nq, k), dtype=np.uint32)
+            sc = np.empty((nq, k), dtype=np.int32 if self.is_int else np.float32)
+            cnt = np.empty((nq,), dtype=np.int32)
+        N.check(self._lib.crs_index_search_sharded(self._h, exchange._h, q.ctypes.data_as(C.c_void_p), nq, int(k),
+                                                   float(min_similarity), ids.ctypes.data_as(C.c_void_p),
+                                                   sc.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p)))
+        return ids, sc, cnt
+
+    def search_push(self, exchange, queries, k: int, min_similarity: float = -math.inf) -> None:
+        """First half of a sharded search for a host that drives several GPUs from one thread: local
+        search + stores into every peer's receive buffer; waits for nobody (torch CUDA queries)."""
+        q = queries if queries.dim() == 2 else queries[None, :]
+        q = q.contiguous()
+        self._use_torch_stream()
+        N.check(self._lib.crs_index_search_push(self._h, exchange._h, C.c_void_p(q.data_ptr()), q.shape[0], int(k),
+                                                float(min_similarity)))
+
     def capture_search(self, nq: int, k: int, min_similarity: float = -math.inf):
         """CUDA-graph form of the device-buffer search for latency-bound callers (a single query over a
         small shard is ~5 short kernels: their launch cost, not their run time, bounds the call).

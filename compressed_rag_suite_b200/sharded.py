@@ -54,10 +54,118 @@ def exchange_candidates(packed, group=None):
     return out
 
 
-class ShardedSearcher:
-    """Wraps this rank's ShardIndex; ``search`` returns the GLOBAL top-k on every rank."""
+class PeerExchange:
+    """One rank's ``crs_exchange``: a receive buffer every peer GPU stores its local top-k into (NVLink
+    peer memory), so that the exchange + merge of a sharded search is one kernel of libcrs instead of an
+    NCCL allgather launch followed by a merge launch.  Wiring the peers is the only host-side step:
 
-    def __init__(self, index, group=None, local_only: bool = False):
+    * ranks in different processes (torchrun): ``PeerExchange.from_process_group`` allgathers the 64-byte
+      CUDA IPC handles of the receive buffers through torch.distributed and maps them;
+    * ranks in one process (one host thread driving several GPUs): ``PeerExchange.wire_local``.
+    """
+
+    def __init__(self, device: int, rank: int, world: int, max_nq: int, max_k: int):
+        import ctypes as C
+        from . import _native as N
+        self._lib = N.lib()
+        self._h = C.c_void_p()
+        N.check(self._lib.crs_exchange_create(C.byref(self._h), int(device), int(rank), int(world), int(max_nq), int(max_k)))
+        self.device, self.rank, self.world, self.max_nq, self.max_k = int(device), int(rank), int(world), int(max_nq), int(max_k)
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.crs_exchange_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def ipc_handle(self) -> bytes:
+        import ctypes as C
+        from . import _native as N
+        buf = (C.c_uint8 * 64)()
+        N.check(self._lib.crs_exchange_ipc_handle(self._h, buf))
+        return bytes(buf)
+
+    def open_peers(self, handles: bytes) -> None:
+        import ctypes as C
+        from . import _native as N
+        if len(handles) != 64 * self.world:
+            raise ValueError("handles must hold world x 64 bytes")
+        N.check(self._lib.crs_exchange_open_peers(self._h, C.c_char_p(handles)))
+
+    def buffer(self) -> int:
+        import ctypes as C
+        from . import _native as N
+        p = C.c_void_p()
+        N.check(self._lib.crs_exchange_buffer(self._h, C.byref(p)))
+        return p.value
+
+    def status(self):
+        """-> (timed_out: bool, step: int) after the current stream has drained."""
+        import ctypes as C
+        import torch
+        from . import _native as N
+        t, s = C.c_int(), C.c_uint32()
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        N.check(self._lib.crs_exchange_status(self._h, C.c_void_p(st), C.byref(t), C.byref(s)))
+        return bool(t.value), int(s.value)
+
+    def merge(self, nq: int, k: int, is_int: bool):
+        """Second half of a split sharded search (see ShardIndex.search_push): wait for the peers' pushes of
+        this step and merge -> (ids, scores, counts) CUDA tensors on this exchange's device."""
+        import ctypes as C
+        import torch
+        from . import _native as N
+        dev = torch.device("cuda", self.device)
+        ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
+        sc = torch.empty((nq, k), dtype=torch.int32 if is_int else torch.float32, device=dev)
+        cnt = torch.empty((nq,), dtype=torch.int32, device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        N.check(self._lib.crs_exchange_merge(self._h, C.c_void_p(st), int(nq), int(k), int(is_int), C.c_void_p(ids.data_ptr()),
+                                             C.c_void_p(sc.data_ptr()), C.c_void_p(cnt.data_ptr())))
+        return ids, sc, cnt
+
+    @classmethod
+    def from_process_group(cls, device: int, max_nq: int, max_k: int, group=None) -> "PeerExchange":
+        """Collective: every rank of the group creates its exchange and maps every peer's receive buffer."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        ex = cls(device, rank, world, max_nq, max_k)
+        mine = torch.frombuffer(bytearray(ex.ipc_handle()), dtype=torch.uint8).to(torch.device("cuda", device))
+        allh = torch.empty((world, 64), dtype=torch.uint8, device=mine.device)
+        dist.all_gather_into_tensor(allh, mine, group=group)
+        ex.open_peers(bytes(allh.cpu().numpy().tobytes()))
+        dist.barrier(group=group)
+        return ex
+
+    @staticmethod
+    def wire_local(exchanges) -> None:
+        """Single process: exchanges[r] is rank r's exchange (one per device); gives every rank the others'
+        receive buffers (peer access between the devices is enabled by the library)."""
+        import ctypes as C
+        from . import _native as N
+        world = len(exchanges)
+        bufs = (C.c_void_p * world)(*[C.c_void_p(e.buffer()) for e in exchanges])
+        for e in exchanges:
+            if e.world != world:
+                raise ValueError("every exchange must be created for the same world size")
+            N.check(e._lib.crs_exchange_set_peer_buffers(e._h, bufs))
+
+
+class ShardedSearcher:
+    """Wraps this rank's ShardIndex; ``search`` returns the GLOBAL top-k on every rank.
+
+    exchange: "peer" (default on CUDA with world > 1) — the library's one-kernel exchange + merge over NVLink
+    peer memory; "nccl" — ``all_gather_into_tensor`` of the packed candidates followed by the merge kernel K7
+    (the only form that also runs on gloo / CPU tensors).  Both return identical results."""
+
+    def __init__(self, index, group=None, local_only: bool = False, exchange: str = "peer",
+                 max_nq: int = 1024, max_k: int = 128):
         """local_only: the index holds the whole corpus; never exchange (even inside a process group)."""
         import torch.distributed as dist
         self.index = index
@@ -65,6 +173,21 @@ class ShardedSearcher:
         self.local_only = local_only
         self.world = 1 if local_only else (dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1)
         self.merge_launches = 0
+        if exchange not in ("peer", "nccl"):
+            raise ValueError("exchange must be 'peer' or 'nccl'")
+        self.exchange = exchange
+        self._peer = None
+        self._peer_cap = (int(max_nq), int(max_k))
+
+    def _peer_exchange(self, nq: int, k: int):
+        """(Re)create the peer exchange when a search exceeds its capacity — a collective step: every rank
+        sees the same nq and k, so every rank takes it together."""
+        if self._peer is None or nq > self._peer.max_nq or k > self._peer.max_k:
+            if self._peer is not None:
+                self._peer.close()
+            cap_nq, cap_k = max(nq, self._peer_cap[0]), min(128, max(k, self._peer_cap[1]))
+            self._peer = PeerExchange.from_process_group(self.index.device, cap_nq, cap_k, self.group)
+        return self._peer
 
     def search(self, queries, k: int, min_similarity: float = -math.inf):
         """queries: float32 CUDA tensor [nq, dim], the same on every rank.
@@ -74,6 +197,10 @@ class ShardedSearcher:
         if self.world == 1:
             self.merge_launches = 0
             return self.index.search(queries, k, min_similarity)
+        if self.exchange == "peer" and queries.is_cuda:
+            nq = queries.shape[0] if queries.dim() > 1 else 1
+            self.merge_launches = 0                      # the exchange kernel is counted by the library
+            return self.index.search_sharded(self._peer_exchange(nq, k), queries, k, min_similarity)
         # the local result is written straight into the send buffer ([0] ids, [1] raw-score bits) and the
         # merge reads the gathered buffer in place: search -> allgather -> merge, no pack / unpack copies
         nq = queries.shape[0] if queries.dim() > 1 else 1
@@ -83,6 +210,33 @@ class ShardedSearcher:
         gathered = exchange_candidates(send, self.group)             # [G, 2, nq, k]
         self.merge_launches = 1
         return merge_gathered(gathered, nq, k, k, self.index.is_int)
+
+    def capture(self, nq: int, k: int, min_similarity: float = -math.inf):
+        """The whole sharded step — encode, local search, exchange, merge — as ONE CUDA graph (peer exchange
+        only: nothing in it is a library collective).  Returns a GraphedSearch: copy the queries into
+        ``.queries``, ``.replay()``, read ``.ids / .scores / .counts``.  Every rank must capture and replay in
+        step; the index must not grow while the graph is in use."""
+        import torch
+        from .index import GraphedSearch
+        if self.world > 1 and self.exchange != "peer":
+            raise ValueError("capture needs the peer exchange")
+        ix = self.index
+        dev = torch.device("cuda", ix.device)
+        q = torch.zeros((nq, ix.dim), dtype=torch.float32, device=dev)
+        ex = self._peer_exchange(nq, k) if self.world > 1 else None
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                      # warm-up sizes every scratch buffer (and takes two steps on every rank)
+            for _ in range(2):
+                self.search(q, k, min_similarity)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        ix.set_option("profiling", 0)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            ids, sc, cnt = self.search(q, k, min_similarity)
+        ix._use_torch_stream()
+        return GraphedSearch(graph, q, ids, sc, cnt, len(ix))
 
 
 # ------------------------------------------------------------------------------------------

@@ -75,7 +75,8 @@ int crs_index_set_stream(crs_index* idx, void* cuda_stream);
 
 /* replaces collection.add(embeddings=...) — rag/indexing.py:114-119 (the
  * ids/documents/metadatas of that call stay with the Python host).
- *   rows: [n, dim] row-major, src_dtype must be CRS_F32; host or device. */
+ *   rows: [n, dim] row-major, src_dtype must be CRS_F32; host or device.
+ * Inner-product space (CRS_IP) needs a float store: I8 / B1 codes are defined on unit rows. */
 int crs_index_add(crs_index* idx, const void* rows, int64_t n, crs_dtype src_dtype);
 /* replaces collection.count() — rag/indexing.py:52,120,147,152,206 */
 int crs_index_count(const crs_index* idx, int64_t* out_count);
@@ -107,7 +108,9 @@ int crs_index_last_stats(const crs_index* idx, crs_search_stats* out);
  *   "gemm_min_nq"   [2]  smallest batch that takes the contraction
  *   "gemm_cluster"  [0]  0 auto (2 query tiles per TMA-multicast cluster), 1 | 2 | 4, 22 = CTA-pair MMA (cta_group::2)
  *   "gemm_prefetch" [0]  corpus tiles prefetched into L2 ahead of the TMA ring
- *   "sample_rows"   [65536] rows of the sample pass that seeds the contraction's per-query thresholds (0 = off)
+ *   "share_floor"   [1]  contraction: the corpus slices of a query share their k-th best score while the launch runs
+ *   "gemm_warm"     [8]  contraction: first tiles of every slice that only seed the floor and are computed again last
+ *   "sample_rows"   [0]  rows of an optional sample pass that seeds the contraction's per-query floors (0 = off)
  *   "multi_scan"    [8]  largest group of short-row integer queries that shares one corpus pass (<= 1 = off)
  *   "short_lists"   [1]  integer scans with k > 32 keep 32 keys per CTA + certification (0 = full 128-key lists)
  *   "force_exact"   [0]  1 = skip the fast pass of float stores, always run the exhaustive fp64 pass
@@ -185,6 +188,37 @@ int crs_merge_topk(void* cuda_stream, const uint32_t* ids, const void* scores, i
 int crs_merge_topk_strided(void* cuda_stream, const uint32_t* ids, const void* scores, int is_int,
                            int n_lists, int nq, int k_in, int k_out, int64_t list_stride,
                            uint32_t* out_ids, void* out_scores, int32_t* out_counts);
+
+/* ---- cross-shard exchange over NVLink peer memory (no reference counterpart: the reference is single-node).
+ * The sharded search of the north star — local top-k per GPU, exchange of the k*(id, score) candidates, final
+ * merge — as ONE kernel after the local search: every rank stores its [nq, k] lists straight into every
+ * peer's receive buffer (peer-mapped global memory), flags them, waits for the peers' flags and merges.
+ * The NCCL form (allgather + crs_merge_topk[_strided]) stays available; both give identical results.
+ *
+ *   one crs_exchange per rank (= per GPU), sized for the largest nq and k it will carry (k <= 128);
+ *   ranks in different processes:  crs_exchange_ipc_handle -> allgather the 64-byte handles with any host
+ *                                  mechanism (torch.distributed, MPI, a file) -> crs_exchange_open_peers;
+ *   ranks in one process:          crs_exchange_buffer of every rank -> crs_exchange_set_peer_buffers
+ *                                  (enables peer access between the devices).
+ * Every rank must run the same sequence of sharded searches (same nq and k per step). */
+typedef struct crs_exchange crs_exchange;
+int crs_exchange_create(crs_exchange** out, int device, int rank, int world, int max_nq, int max_k);
+int crs_exchange_destroy(crs_exchange* ex);
+int crs_exchange_ipc_handle(crs_exchange* ex, void* out_handle64);
+int crs_exchange_open_peers(crs_exchange* ex, const void* handles /* world x 64 bytes, rank order */);
+int crs_exchange_buffer(crs_exchange* ex, void** out_ptr);
+int crs_exchange_set_peer_buffers(crs_exchange* ex, void* const* bufs /* world device pointers, rank order */);
+/* waits for `cuda_stream`, then reports the step stamp and whether any wait for a peer timed out (~2 s) */
+int crs_exchange_status(crs_exchange* ex, void* cuda_stream, int* timed_out, uint32_t* step);
+/* crs_index_search on this rank's shard + exchange + merge: every rank ends with the GLOBAL top-k
+ * (same buffers and conventions as crs_index_search). */
+int crs_index_search_sharded(crs_index* idx, crs_exchange* ex, const void* queries, int nq, int k,
+                             float min_similarity, uint32_t* out_ids, void* out_scores, int32_t* out_counts);
+/* the same in two calls, for a host that drives several GPUs from one thread: push = local search + stores
+ * to the peers (waits for nobody); merge = wait for the peers' pushes of this step + merge (device buffers). */
+int crs_index_search_push(crs_index* idx, crs_exchange* ex, const void* queries, int nq, int k, float min_similarity);
+int crs_exchange_merge(crs_exchange* ex, void* cuda_stream, int nq, int k, int is_int,
+                       uint32_t* out_ids, void* out_scores, int32_t* out_counts);
 
 /* replaces chromadb.PersistentClient(path) persistence + get_collection reload —
  * rag/indexing.py:32-34,46-55.  Raw code blob + small header; the host keeps

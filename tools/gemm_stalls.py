@@ -19,7 +19,7 @@ def run(n, dim, nq, k, store, cluster):
     ix.set_option("gemm_cluster", cluster)
     ix.set_option("profiling", 1)
     lib = N.lib()
-    buf = (C.c_ulonglong * 8)()
+    buf = (C.c_ulonglong * 32)()
     for _ in range(5):
         ix.search(q, k)
     torch.cuda.synchronize()
@@ -29,15 +29,26 @@ def run(n, dim, nq, k, store, cluster):
     torch.cuda.synchronize()
     lib.crs_debug_gemm_profile(buf, 1)
     wf, we, tot, cnt = buf[0], buf[1], buf[2], buf[3]
-    print(f"{store} nq={nq} k={k} cluster={cluster}: kernel_ms={ix.last_kernel_ms():.3f} issuers={cnt} "
-          f"wait_operands={wf / tot:.3f} wait_accumulator_drained={we / tot:.3f} of issuer time", flush=True)
+    ewait, etot, ecnt, tiles = buf[4], buf[5], buf[6], buf[7]
+    print(f"{store} n={n} nq={nq} k={k} cluster={cluster} grid={ix.last_stats()['grid']}: kernel_ms={ix.last_kernel_ms():.3f} issuers={cnt} "
+          f"wait_operands={wf / tot:.3f} wait_accumulator_drained={we / tot:.3f} of issuer time; "
+          f"issuer cycles/tile={tot / max(tiles, 1):.0f} (issuing {(tot - wf - we) / max(tiles, 1):.0f}); "
+          f"epilogue warp: cycles/tile={etot / max(ecnt, 1) / (tiles / max(cnt, 1)):.0f}, waiting for an accumulator {ewait / max(etot, 1):.3f}",
+          flush=True)
+    pts = [0] + [1 << j for j in range(14)]
+    curve = [(pts[j], round(buf[8 + j] / max(cnt, 1))) for j in range(15) if buf[8 + j]]
+    hp = buf[24:32]
+    if hp[2]:
+        print(f"   floor helper: {hp[0] / hp[2]:.1f} rounds per CTA, {hp[1] / max(hp[0], 1):.0f} cycles per round, first floor stored at cycle "
+              f"{hp[3] / max(hp[4], 1):.0f} ({hp[4]} of {hp[2]} helpers stored one)", flush=True)
+    print("   progress (tile index: cycles since CTA start when the issuer begins it):", curve, "end:", round(buf[23] / max(cnt, 1)), flush=True)
     ix.close()
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "shard":          # the per-GPU work of the 8-GPU headline run
         run(1_250_000, 384, 1024, 10, "f16", 2)
         run(1_250_000, 384, 1024, 10, "i8", 2)
-        run(10_000_000, 384, 1024, 10, "f16", 2)
+        run(10_000_000, 384, 1024, 10, "i8", 2)
         sys.exit(0)
     run(10_000_000, 384, 1024, 10, "f16", 2)
     run(10_000_000, 384, 1024, 10, "f16", 22)

@@ -49,10 +49,25 @@ def main():
         full.add(x)
         shard = ShardIndex(dim, dtype=store, device=local, row_base=lo)
         shard.add(x[lo:hi])
+        peer = ShardedSearcher(shard, exchange="peer", max_nq=512)
+        nccl = ShardedSearcher(shard, exchange="nccl")
         for thr in (-float("inf"), 0.3):
             want = full.search(q, k, thr)
-            got = ShardedSearcher(shard).search(q, k, thr)
-            report(f"top-{k} {store} n={n} nq={nq} thr={thr}", same(got, want))
+            report(f"top-{k} {store} n={n} nq={nq} thr={thr} [peer-memory exchange kernel]", same(peer.search(q, k, thr), want))
+            report(f"top-{k} {store} n={n} nq={nq} thr={thr} [NCCL allgather + merge]", same(nccl.search(q, k, thr), want))
+        # the whole sharded step replayed from one CUDA graph, with fresh queries copied in between replays
+        want = full.search(q, k)
+        gs = peer.capture(nq, k)
+        ok = True
+        for rep in range(3):
+            qq = torch.roll(q, rep, 0)
+            gs.queries.copy_(qq)
+            got = gs.replay()
+            torch.cuda.synchronize()
+            ok &= same(got, full.search(qq, k))
+        report(f"top-{k} {store} n={n} nq={nq} [sharded step as one CUDA graph, 3 replays]", ok)
+        timed_out, step = peer._peer.status()
+        report(f"exchange of {store}: no wait timed out (step {step})", not timed_out)
         if store in ("f16", "i8"):
             m = ShardedMMRSearcher(shard)
             w = ShardedMMRSearcher(full, local_only=True)

@@ -41,6 +41,10 @@ def main():
     z /= z.norm(dim=1, keepdim=True)
     q = (0.6 * cen[torch.randint(0, 4096, (nq,), device="cuda", generator=g)] + 0.8 * z).contiguous()
     ix.set_option("profiling", 1)
+    opts = os.environ.get("CRS_OPTS", "")
+    for kv in filter(None, opts.split(",")):                  # e.g. CRS_OPTS=share_floor=0,sample_rows=65536
+        name, val = kv.split("=")
+        ix.set_option(name, int(val))
     for _ in range(5):
         ix.search(q, k)
     torch.cuda.synchronize()
@@ -55,7 +59,7 @@ def main():
     st = ix.last_stats()
     out = {"store": store, "rows": n, "dim": dim, "nq": nq, "k": k, "step_ms": round(step, 4),
            "kernel_ms": round(sum(kms) / len(kms), 4), "outside_kernel_ms": round(step - sum(kms) / len(kms), 4),
-           "launches": st["kernel_launches"], "path": st["path"]}
+           "launches": st["kernel_launches"], "path": st["path"], "opts": opts, "uncertified": st["uncertified_total"]}
     # the same step replayed from a CUDA graph (no host launch gaps)
     try:
         gs = ix.capture_search(nq, k)
