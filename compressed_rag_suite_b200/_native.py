@@ -57,9 +57,12 @@ SYMBOLS = {
     "crs_exchange_set_peer_buffers": (C.c_int, [_P, C.POINTER(_P)]),
     "crs_exchange_status": (C.c_int, [_P, _P, C.POINTER(C.c_int), C.POINTER(C.c_uint32)]),
     "crs_index_search_sharded": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_float, _P, _P, _P]),
-    "crs_index_search_push": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_float]),
+    "crs_index_search_push": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_float, _P]),
+    "crs_index_map_ids": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_uint32]),
     "crs_exchange_merge": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "crs_index_save": (C.c_int, [_P, C.c_char_p]),
+    "crs_index_append": (C.c_int, [_P, C.c_char_p]),
+    "crs_index_truncate": (C.c_int, [_P, C.c_int64]),
     "crs_index_load": (C.c_int, [C.POINTER(_P), C.c_char_p, C.c_int, C.c_uint32]),
 }
 

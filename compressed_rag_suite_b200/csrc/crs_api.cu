@@ -8,6 +8,8 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <sys/types.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <mutex>
@@ -99,6 +101,8 @@ struct crs_index {
     size_t row_bytes = 0;
     int64_t count = 0, capacity = 0, reserve_hint = 0;
     uint8_t* codes = nullptr;
+    uint32_t* id_map = nullptr;        // optional: global id of every local row (crs_index_map_ids); else row_base + row
+    int64_t id_map_cap = 0;
     float i8_scale = 1.0f;
     float row_norm_bound = 1.00390625f;
     cudaStream_t stream = nullptr;
@@ -204,6 +208,10 @@ __global__ void fill_pad_kernel(uint32_t* ids, void* scores, int32_t* counts, in
     }
     if (i < nq) counts[i] = 0;
 }
+__global__ void iota_ids_kernel(uint32_t* dst, int64_t n, uint32_t first) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = first + (uint32_t)i;
+}
 __global__ void set_flags_kernel(int32_t* flags, int nq, int v) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nq) flags[i] = v;
@@ -265,6 +273,7 @@ int crs_index_destroy(crs_index* ix) {
         DeviceGuard g(ix->device);
         cudaStreamSynchronize(ix->stream);
         if (ix->codes) cudaFree(ix->codes);
+        if (ix->id_map) cudaFree(ix->id_map);
         if (ix->n_flagged) cudaFree(ix->n_flagged);
         for (auto& p : ix->evs) { if (p[0]) cudaEventDestroy(p[0]); if (p[1]) cudaEventDestroy(p[1]); }
         if (ix->ev_switch) cudaEventDestroy(ix->ev_switch);
@@ -367,6 +376,36 @@ int crs_index_add(crs_index* ix, const void* rows, int64_t n, crs_dtype src_dtyp
 int crs_index_count(const crs_index* ix, int64_t* out_count) {
     if (!ix || !out_count) return fail(CRS_EINVAL, "bad argument");
     *out_count = ix->count;
+    return CRS_OK;
+}
+
+int crs_index_map_ids(crs_index* ix, int64_t first_row, int64_t n, uint32_t first_global_id) {
+    if (!ix) return fail(CRS_EINVAL, "index is NULL");
+    if (first_row < 0 || n < 0 || first_row + n > ix->count) return fail(CRS_EINVAL, "row range outside the index");
+    if ((uint64_t)first_global_id + (uint64_t)n >= 0xFFFFFFFFull) return fail(CRS_EINVAL, "row ids would overflow uint32");
+    if (n == 0) return CRS_OK;
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = ix->stream;
+    if (ix->id_map_cap < ix->capacity) {                    // (re)allocate beside the codes; unmapped rows keep row_base + row
+        uint32_t* p = nullptr;
+        CRS_CUDA(cudaMalloc(&p, (size_t)ix->capacity * sizeof(uint32_t)));
+        cudaError_t e = cudaSuccess;
+        if (ix->id_map) e = cudaMemcpyAsync(p, ix->id_map, (size_t)ix->id_map_cap * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st);
+        const int64_t have = ix->id_map ? ix->id_map_cap : 0;
+        if (e == cudaSuccess && ix->capacity > have) {
+            iota_ids_kernel<<<(unsigned)((ix->capacity - have + 255) / 256), 256, 0, st>>>(p + have, ix->capacity - have,
+                                                                                         ix->row_base + (uint32_t)have);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { cudaFree(p); return cuda_fail(e, "crs_index_map_ids"); }
+        if (ix->id_map) cudaFree(ix->id_map);
+        ix->id_map = p;
+        ix->id_map_cap = ix->capacity;
+    }
+    iota_ids_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ix->id_map + first_row, n, first_global_id);
+    CRS_CUDA(cudaGetLastError());
     return CRS_OK;
 }
 
@@ -547,7 +586,7 @@ static int search_impl(crs_index* ix, const void* queries, int nq, int k, float 
         fa.codes = ix->codes; fa.qcodes = ix->qcodes.p; fa.qnorms = ix->qnorms.p;
         fa.dim_padded = ix->dim_padded; fa.bf16 = ix->store == CRS_BF16;
         fa.row_norm_bound = ix->row_norm_bound;
-        fa.min_similarity = min_similarity; fa.row_base = ix->row_base;
+        fa.min_similarity = min_similarity; fa.row_base = ix->row_base; fa.id_map = ix->id_map;
         fa.out_ids = d_ids; fa.out_scores = d_scores; fa.out_counts = d_counts;
         fa.flags = ix->flags.p; fa.n_flagged = ix->n_flagged; fa.is_int = is_int;
 
@@ -1038,9 +1077,10 @@ int crs_index_search_sharded(crs_index* ix, crs_exchange* ex, const void* querie
     return search_impl(ix, queries, nq, k, min_similarity, nullptr, out_ids, out_scores, out_counts, ex, 0);
 }
 
-int crs_index_search_push(crs_index* ix, crs_exchange* ex, const void* queries, int nq, int k, float min_similarity) {
+int crs_index_search_push(crs_index* ix, crs_exchange* ex, const void* queries, int nq, int k, float min_similarity,
+                          const uint32_t* allow_bits) {
     if (!ex) return fail(CRS_EINVAL, "exchange is NULL");
-    return search_impl(ix, queries, nq, k, min_similarity, nullptr, nullptr, nullptr, nullptr, ex, 1);
+    return search_impl(ix, queries, nq, k, min_similarity, allow_bits, nullptr, nullptr, nullptr, ex, 1);
 }
 
 int crs_exchange_merge(crs_exchange* ex, void* cuda_stream, int nq, int k, int is_int,
@@ -1076,29 +1116,86 @@ struct CrsFileHeader {
 };
 static_assert(sizeof(CrsFileHeader) == 64, "header is 64 bytes");
 
-int crs_index_save(crs_index* ix, const char* path) {
-    if (!ix || !path) return fail(CRS_EINVAL, "bad argument");
-    std::lock_guard<std::mutex> lk(ix->mu);
-    DeviceGuard g(ix->device);
-    FILE* f = fopen(path, "wb");
-    if (!f) return fail(CRS_EIO, std::string("cannot open ") + path);
-    CrsFileHeader h{};
-    memcpy(h.magic, "CRSIDX1", 8);
-    h.dim = ix->dim; h.dim_padded = ix->dim_padded; h.store = ix->store; h.metric = ix->metric;
-    h.count = ix->count; h.i8_scale = ix->i8_scale; h.row_norm_bound = ix->row_norm_bound;
-    bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
+// rows [from_row, count) of the index -> f at its current position
+static int write_rows(crs_index* ix, FILE* f, int64_t from_row) {
     const size_t chunk_rows = std::max<size_t>(1, (64u << 20) / ix->row_bytes);
     std::vector<uint8_t> buf(chunk_rows * ix->row_bytes);
-    for (int64_t off = 0; ok && off < ix->count; off += (int64_t)chunk_rows) {
+    for (int64_t off = from_row; off < ix->count; off += (int64_t)chunk_rows) {
         const size_t m = (size_t)std::min<int64_t>((int64_t)chunk_rows, ix->count - off);
         cudaError_t e = cudaMemcpyAsync(buf.data(), ix->codes + (size_t)off * ix->row_bytes, m * ix->row_bytes,
                                         cudaMemcpyDeviceToHost, ix->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
-        if (e != cudaSuccess) { fclose(f); return cuda_fail(e, "cudaMemcpy"); }
-        ok = fwrite(buf.data(), ix->row_bytes, m, f) == m;
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
+        if (fwrite(buf.data(), ix->row_bytes, m, f) != m) return fail(CRS_EIO, "write failed");
     }
-    ok = (fclose(f) == 0) && ok;
-    return ok ? CRS_OK : fail(CRS_EIO, std::string("write failed: ") + path);
+    return CRS_OK;
+}
+
+static bool flush_to_disk(FILE* f) { return fflush(f) == 0 && fsync(fileno(f)) == 0; }
+
+static void fill_header(const crs_index* ix, CrsFileHeader* h) {
+    memset(h, 0, sizeof(*h));
+    memcpy(h->magic, "CRSIDX1", 8);
+    h->dim = ix->dim; h->dim_padded = ix->dim_padded; h->store = ix->store; h->metric = ix->metric;
+    h->count = ix->count; h->i8_scale = ix->i8_scale; h->row_norm_bound = ix->row_norm_bound;
+}
+
+// Whole index -> path, atomically: written to "<path>.tmp", flushed to disk, renamed over the old file.
+// A crash leaves either the old file or the new one, never a truncated mix.
+int crs_index_save(crs_index* ix, const char* path) {
+    if (!ix || !path) return fail(CRS_EINVAL, "bad argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    const std::string tmp = std::string(path) + ".tmp";
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) return fail(CRS_EIO, std::string("cannot open ") + tmp);
+    CrsFileHeader h;
+    fill_header(ix, &h);
+    int rc = fwrite(&h, sizeof(h), 1, f) == 1 ? CRS_OK : fail(CRS_EIO, "write failed");
+    if (rc == CRS_OK) rc = write_rows(ix, f, 0);
+    if (rc == CRS_OK && !flush_to_disk(f)) rc = fail(CRS_EIO, std::string("flush failed: ") + tmp);
+    if (fclose(f) != 0 && rc == CRS_OK) rc = fail(CRS_EIO, std::string("close failed: ") + tmp);
+    if (rc == CRS_OK && rename(tmp.c_str(), path) != 0) rc = fail(CRS_EIO, std::string("rename failed: ") + path);
+    if (rc != CRS_OK) remove(tmp.c_str());
+    return rc;
+}
+
+// Appends the rows the file does not hold yet (incremental indexing: O(new rows), not O(all rows) per add).
+// Order: new rows are written behind the old ones and flushed, THEN the header's row count is advanced and
+// flushed — a crash in between leaves a file whose header still describes a consistent prefix.
+int crs_index_append(crs_index* ix, const char* path) {
+    if (!ix || !path) return fail(CRS_EINVAL, "bad argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    FILE* f = fopen(path, "r+b");
+    if (!f) return fail(CRS_EIO, std::string("cannot open ") + path);
+    CrsFileHeader h{};
+    int rc = CRS_OK;
+    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "CRSIDX1", 8) != 0) rc = fail(CRS_EIO, "not a CRS index file");
+    if (rc == CRS_OK && (h.dim != ix->dim || h.dim_padded != ix->dim_padded || h.store != (int32_t)ix->store ||
+                         h.metric != (int32_t)ix->metric))
+        rc = fail(CRS_EIO, "file holds an index of another shape");
+    if (rc == CRS_OK && (h.count < 0 || h.count > ix->count)) rc = fail(CRS_EIO, "file holds more rows than the index");
+    if (rc == CRS_OK && fseeko(f, (off_t)sizeof(h) + (off_t)h.count * (off_t)ix->row_bytes, SEEK_SET) != 0)
+        rc = fail(CRS_EIO, "seek failed");
+    if (rc == CRS_OK) rc = write_rows(ix, f, h.count);
+    if (rc == CRS_OK && !flush_to_disk(f)) rc = fail(CRS_EIO, "flush failed");
+    if (rc == CRS_OK) {
+        fill_header(ix, &h);
+        if (fseeko(f, 0, SEEK_SET) != 0 || fwrite(&h, sizeof(h), 1, f) != 1 || !flush_to_disk(f))
+            rc = fail(CRS_EIO, "header update failed");
+    }
+    fclose(f);
+    return rc;
+}
+
+// Drops the rows from new_count on (a host whose sidecar holds fewer rows than the blob after a crash).
+int crs_index_truncate(crs_index* ix, int64_t new_count) {
+    if (!ix) return fail(CRS_EINVAL, "index is NULL");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    if (new_count < 0 || new_count > ix->count) return fail(CRS_EINVAL, "new_count out of range");
+    ix->count = new_count;
+    return CRS_OK;
 }
 
 int crs_index_load(crs_index** out, const char* path, int device, uint32_t row_base) {
@@ -1111,22 +1208,36 @@ int crs_index_load(crs_index** out, const char* path, int device, uint32_t row_b
         fclose(f);
         return fail(CRS_EIO, "not a CRS index file");
     }
+    // the header is untrusted input: every field is checked against what this library can hold and against
+    // the size of the file (a row count beyond the rows actually present is clamped: torn append)
+    if (h.dim <= 0 || h.count < 0 || (h.store != CRS_F16 && h.store != CRS_BF16 && h.store != CRS_I8 && h.store != CRS_B1) ||
+        (h.metric != CRS_COSINE && h.metric != CRS_IP) || !(h.i8_scale > 0.f) || !(h.row_norm_bound > 0.f)) {
+        fclose(f);
+        return fail(CRS_EIO, "corrupt index header");
+    }
+    const int dp = padded_dim_for(h.dim, (crs_dtype)h.store);
+    if (dp < 0 || dp != h.dim_padded) { fclose(f); return fail(CRS_EIO, "layout mismatch"); }
+    const size_t rb = row_bytes_for(dp, (crs_dtype)h.store);
+    int64_t rows_in_file = 0;
+    if (fseeko(f, 0, SEEK_END) == 0) rows_in_file = ((int64_t)ftello(f) - (int64_t)sizeof(h)) / (int64_t)rb;
+    if (fseeko(f, (off_t)sizeof(h), SEEK_SET) != 0) { fclose(f); return fail(CRS_EIO, "seek failed"); }
+    const int64_t count = std::max<int64_t>(0, std::min<int64_t>(h.count, rows_in_file));
+    if ((uint64_t)row_base + (uint64_t)count >= 0xFFFFFFFFull) { fclose(f); return fail(CRS_EIO, "row ids would overflow uint32"); }
     crs_index* ix = nullptr;
-    int rc = crs_index_create(&ix, h.dim, (crs_dtype)h.store, (crs_metric)h.metric, device, row_base, h.count);
+    int rc = crs_index_create(&ix, h.dim, (crs_dtype)h.store, (crs_metric)h.metric, device, row_base, count);
     if (rc != CRS_OK) { fclose(f); return rc; }
-    if (ix->dim_padded != h.dim_padded) { fclose(f); crs_index_destroy(ix); return fail(CRS_EIO, "layout mismatch"); }
     ix->i8_scale = h.i8_scale; ix->row_norm_bound = h.row_norm_bound;
     DeviceGuard g(device);
     const size_t chunk_rows = std::max<size_t>(1, (64u << 20) / ix->row_bytes);
     std::vector<uint8_t> buf(chunk_rows * ix->row_bytes);
-    for (int64_t off = 0; off < h.count; off += (int64_t)chunk_rows) {
-        const size_t m = (size_t)std::min<int64_t>((int64_t)chunk_rows, h.count - off);
+    for (int64_t off = 0; off < count; off += (int64_t)chunk_rows) {
+        const size_t m = (size_t)std::min<int64_t>((int64_t)chunk_rows, count - off);
         if (fread(buf.data(), ix->row_bytes, m, f) != m) { fclose(f); crs_index_destroy(ix); return fail(CRS_EIO, "short read"); }
         cudaError_t e = cudaMemcpy(ix->codes + (size_t)off * ix->row_bytes, buf.data(), m * ix->row_bytes, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { fclose(f); crs_index_destroy(ix); return cuda_fail(e, "cudaMemcpy"); }
     }
     fclose(f);
-    ix->count = h.count;
+    ix->count = count;
     *out = ix;
     return CRS_OK;
 }

@@ -61,6 +61,7 @@ struct FinalizeArgs {
     float row_norm_bound;
     float min_similarity;      // float-domain threshold on the exact score (mode 0 only)
     uint32_t row_base;
+    const uint32_t* id_map;    // optional: global id of every local row (else row_base + row)
     uint32_t* out_ids;         // [nq][k]
     void* out_scores;          // [nq][k] f32 or i32 raw
     int32_t* out_counts;       // [nq]

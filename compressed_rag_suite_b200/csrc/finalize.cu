@@ -242,7 +242,9 @@ finalize_kernel(FinalizeArgs a) {
         if (i < a.k) {
             const bool ok = i < count;
             const uint64_t key = x[s];
-            a.out_ids[(size_t)q * a.k + i] = ok ? key_id(key) + a.row_base : CRS_PAD_ID;
+            uint32_t gid = CRS_PAD_ID;
+            if (ok) gid = a.id_map ? a.id_map[key_id(key)] : key_id(key) + a.row_base;
+            a.out_ids[(size_t)q * a.k + i] = gid;
             if (a.is_int) {
                 reinterpret_cast<int32_t*>(a.out_scores)[(size_t)q * a.k + i] =
                     ok ? unorderable_i32(key_ord(key)) : INT32_MIN;

@@ -277,9 +277,16 @@ __device__ __forceinline__ void slab_warm(const uint32_t (&r)[32], uint32_t (&to
 template <int L, bool INT>
 __device__ __forceinline__ void slab_scan(const uint32_t (&r)[32], int64_t row0, int64_t n_rows,
                                           typename ScoreT<INT>::type& tau, uint32_t (&best_ord)[L], uint32_t (&best_nid)[L],
-                                          const uint32_t* __restrict__ allow, bool& dirty) {
+                                          const uint32_t* __restrict__ allow, bool& dirty
+#ifdef CRS_GEMM_PROFILE
+                                          , unsigned& n_slow, unsigned& n_ins
+#endif
+                                          ) {
     using T = typename ScoreT<INT>::type;
     if (slab_max<INT>(r) >= tau) {
+#ifdef CRS_GEMM_PROFILE
+        ++n_slow;
+#endif
         unsigned mask = 0;
         T tmp[32];                           // dynamically indexed -> local memory, touched on this path only
 #pragma unroll
@@ -307,6 +314,9 @@ __device__ __forceinline__ void slab_scan(const uint32_t (&r)[32], int64_t row0,
                 const uint32_t nr = 0xFFFFFFFFu - (uint32_t)row;
                 if (o > best_ord[L - 1] || (o == best_ord[L - 1] && nr > best_nid[L - 1])) {
                     list_insert<L>(best_ord, best_nid, o, nr);
+#ifdef CRS_GEMM_PROFILE
+                    ++n_ins;
+#endif
                     dirty = true;
                     if (best_ord[L - 1] != 0u) tau = smax<T>(tau, from_ord<INT>(best_ord[L - 1]));
                 }
@@ -653,6 +663,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         bool dirty = false;
 #ifdef CRS_GEMM_PROFILE
         long long e_wait = 0, e_begin = clock64();
+        unsigned p_slow = 0, p_ins = 0, p_slow_early = 0, p_ins_early = 0;
 #endif
         for (int it = 0; it < n_iter; ++it) {
             const int buf = it & 1;
@@ -691,11 +702,19 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 #pragma unroll 1
                 for (int slab = 0; slab < kTileC / 32; slab += 2) {
                     tmem_ld32(taddr + (slab + 1) * 32, rb);
-                    slab_scan<L, INT>(ra, row0 + slab * 32, n_rows, tau, best_ord, best_nid, allow, dirty);
+                    slab_scan<L, INT>(ra, row0 + slab * 32, n_rows, tau, best_ord, best_nid, allow, dirty
+#ifdef CRS_GEMM_PROFILE
+                                      , p_slow, p_ins
+#endif
+                                      );
                     __syncwarp();                                   // tcgen05.ld / wait are .aligned: reconverge first
                     tmem_ld_wait();
                     if (slab + 2 < kTileC / 32) tmem_ld32(taddr + (slab + 2) * 32, ra);
-                    slab_scan<L, INT>(rb, row0 + (slab + 1) * 32, n_rows, tau, best_ord, best_nid, allow, dirty);
+                    slab_scan<L, INT>(rb, row0 + (slab + 1) * 32, n_rows, tau, best_ord, best_nid, allow, dirty
+#ifdef CRS_GEMM_PROFILE
+                                      , p_slow, p_ins
+#endif
+                                      );
                     __syncwarp();
                     tmem_ld_wait();
                 }
@@ -718,6 +737,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 }
                 if (floor_ord != 0u) tau = smax<T>(tau, from_ord<INT>(floor_ord));
             }
+#ifdef CRS_GEMM_PROFILE
+            if (it + 1 == n_warm + 8) { p_slow_early = p_slow; p_ins_early = p_ins; }
+#endif
             if (it + 1 == n_warm) {
                 // end of the warm-up: its L-th best group maximum is this slice's first floor; the real list starts empty
                 if (q < nq && best_ord[L - 1] != 0u) tau = smax<T>(tau, from_ord<INT>(best_ord[L - 1]));
@@ -732,6 +754,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             atomicAdd(&g_gemm_prof[4], (unsigned long long)e_wait);
             atomicAdd(&g_gemm_prof[5], (unsigned long long)(clock64() - e_begin));
             atomicAdd(&g_gemm_prof[6], 1ull);
+        }
+        {   // insert-path statistics of every epilogue thread: [5] inserts, [6] slabs on the insert path, [7] the same two
+            // packed for the first 8 tiles after the warm-up (inserts << 32 | slabs)
+            atomicAdd(&g_gemm_hp[5], (unsigned long long)p_ins);
+            atomicAdd(&g_gemm_hp[6], (unsigned long long)p_slow);
+            atomicAdd(&g_gemm_hp[7], ((unsigned long long)p_ins_early << 32) | (unsigned long long)p_slow_early);
         }
 #endif
         if (q < nq) {

@@ -139,9 +139,16 @@ class ShardIndex:
             sc = torch.empty((nq, k), dtype=torch.int32 if self.is_int else torch.float32, device=dev)
             cnt = torch.empty((nq,), dtype=torch.int32, device=dev)
             self._use_torch_stream()
-            N.check(self._lib.crs_index_search(self._h, C.c_void_p(q.data_ptr()), nq, int(k), float(min_similarity),
-                                               C.c_void_p(ids.data_ptr()), C.c_void_p(sc.data_ptr()),
-                                               C.c_void_p(cnt.data_ptr())))
+            if allow is None:
+                N.check(self._lib.crs_index_search(self._h, C.c_void_p(q.data_ptr()), nq, int(k), float(min_similarity),
+                                                   C.c_void_p(ids.data_ptr()), C.c_void_p(sc.data_ptr()),
+                                                   C.c_void_p(cnt.data_ptr())))
+            else:
+                bits = allow if (isinstance(allow, np.ndarray) and allow.dtype == np.uint32) else self.pack_allow(allow)
+                N.check(self._lib.crs_index_search_filtered(self._h, C.c_void_p(q.data_ptr()), nq, int(k),
+                                                            float(min_similarity), bits.ctypes.data_as(C.c_void_p),
+                                                            C.c_void_p(ids.data_ptr()), C.c_void_p(sc.data_ptr()),
+                                                            C.c_void_p(cnt.data_ptr())))
             return ids, sc, cnt
         q = np.ascontiguousarray(queries, dtype=np.float32)
         if q.ndim == 1:
@@ -164,7 +171,10 @@ class ShardIndex:
                                                ids.ctypes.data_as(C.c_void_p), sc.ctypes.data_as(C.c_void_p),
                                                cnt.ctypes.data_as(C.c_void_p)))
         else:
-            bits = self.pack_allow(allow)
+            # a ready-made bitmap (uint32 words, e.g. a cached predicate) or a bool mask over the rows
+            bits = allow if (isinstance(allow, np.ndarray) and allow.dtype == np.uint32) else self.pack_allow(allow)
+            if bits.shape[0] != (len(self) + 31) // 32:
+                raise ValueError("allow bitmap has the wrong number of words")
             N.check(self._lib.crs_index_search_filtered(self._h, q.ctypes.data_as(C.c_void_p), nq, int(k),
                                                         float(min_similarity), bits.ctypes.data_as(C.c_void_p),
                                                         ids.ctypes.data_as(C.c_void_p), sc.ctypes.data_as(C.c_void_p),
@@ -211,14 +221,23 @@ class ShardIndex:
                                                    sc.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p)))
         return ids, sc, cnt
 
-    def search_push(self, exchange, queries, k: int, min_similarity: float = -math.inf) -> None:
+    def search_push(self, exchange, queries, k: int, min_similarity: float = -math.inf, allow=None) -> None:
         """First half of a sharded search for a host that drives several GPUs from one thread: local
-        search + stores into every peer's receive buffer; waits for nobody (torch CUDA queries)."""
+        search + stores into every peer's receive buffer; waits for nobody (torch CUDA queries).
+        allow: optional bool mask / uint32 bitmap over this shard's local rows."""
         q = queries if queries.dim() == 2 else queries[None, :]
         q = q.contiguous()
+        bits = None
+        if allow is not None:
+            bits = allow if (isinstance(allow, np.ndarray) and allow.dtype == np.uint32) else self.pack_allow(allow)
         self._use_torch_stream()
         N.check(self._lib.crs_index_search_push(self._h, exchange._h, C.c_void_p(q.data_ptr()), q.shape[0], int(k),
-                                                float(min_similarity)))
+                                                float(min_similarity),
+                                                bits.ctypes.data_as(C.c_void_p) if bits is not None else None))
+
+    def map_ids(self, first_row: int, n: int, first_global_id: int) -> None:
+        """Local rows [first_row, first_row + n) report the global ids first_global_id.. in searches."""
+        N.check(self._lib.crs_index_map_ids(self._h, int(first_row), int(n), int(first_global_id)))
 
     def capture_search(self, nq: int, k: int, min_similarity: float = -math.inf):
         """CUDA-graph form of the device-buffer search for latency-bound callers (a single query over a
@@ -394,7 +413,15 @@ class ShardIndex:
 
     # ------------------------------------------------------------------ persistence
     def save(self, path: str) -> None:
+        """Whole index -> path, atomically (temp file + rename)."""
         N.check(self._lib.crs_index_save(self._h, path.encode()))
+
+    def append_to(self, path: str) -> None:
+        """Append the rows `path` does not hold yet, then advance its header (crs_index_append)."""
+        N.check(self._lib.crs_index_append(self._h, path.encode()))
+
+    def truncate(self, new_count: int) -> None:
+        N.check(self._lib.crs_index_truncate(self._h, int(new_count)))
 
     @classmethod
     def load(cls, path: str, device: int = 0, row_base: int = 0) -> "ShardIndex":

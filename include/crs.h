@@ -78,6 +78,12 @@ int crs_index_set_stream(crs_index* idx, void* cuda_stream);
  *   rows: [n, dim] row-major, src_dtype must be CRS_F32; host or device.
  * Inner-product space (CRS_IP) needs a float store: I8 / B1 codes are defined on unit rows. */
 int crs_index_add(crs_index* idx, const void* rows, int64_t n, crs_dtype src_dtype);
+/* gives the local rows [first_row, first_row + n) the global ids first_global_id, first_global_id + 1, ...
+ * instead of row_base + row: for a host that deals the rows of one collection out to several indexes in
+ * turns (one GPU each) and still wants the insertion index as the global id.  Ids must grow with the local
+ * row (ties inside a shard go to the lowest LOCAL row).  Searches report the mapped ids;
+ * crs_index_fetch_rows / crs_index_score_rows keep addressing rows as row_base + local row. */
+int crs_index_map_ids(crs_index* idx, int64_t first_row, int64_t n, uint32_t first_global_id);
 /* replaces collection.count() — rag/indexing.py:52,120,147,152,206 */
 int crs_index_count(const crs_index* idx, int64_t* out_count);
 /* dim, padded dim, bytes per stored row, store dtype, metric */
@@ -216,15 +222,23 @@ int crs_index_search_sharded(crs_index* idx, crs_exchange* ex, const void* queri
                              float min_similarity, uint32_t* out_ids, void* out_scores, int32_t* out_counts);
 /* the same in two calls, for a host that drives several GPUs from one thread: push = local search + stores
  * to the peers (waits for nobody); merge = wait for the peers' pushes of this step + merge (device buffers). */
-int crs_index_search_push(crs_index* idx, crs_exchange* ex, const void* queries, int nq, int k, float min_similarity);
+int crs_index_search_push(crs_index* idx, crs_exchange* ex, const void* queries, int nq, int k, float min_similarity,
+                          const uint32_t* allow_bits /* optional row bitmap as in crs_index_search_filtered, NULL = none */);
 int crs_exchange_merge(crs_exchange* ex, void* cuda_stream, int nq, int k, int is_int,
                        uint32_t* out_ids, void* out_scores, int32_t* out_counts);
 
 /* replaces chromadb.PersistentClient(path) persistence + get_collection reload —
  * rag/indexing.py:32-34,46-55.  Raw code blob + small header; the host keeps
  * ids/documents/metadatas in a sidecar. */
+/* whole index -> path, atomically (written to "<path>.tmp", flushed, renamed) */
 int crs_index_save(crs_index* idx, const char* path);
+/* appends the rows `path` does not hold yet and then advances its header (incremental indexing; a crash in
+ * between leaves a consistent prefix) */
+int crs_index_append(crs_index* idx, const char* path);
+/* header fields are validated; a row count beyond the rows present in the file is clamped (torn append) */
 int crs_index_load(crs_index** out, const char* path, int device, uint32_t row_base);
+/* drops the rows from new_count on (a host sidecar that holds fewer rows than the blob after a crash) */
+int crs_index_truncate(crs_index* idx, int64_t new_count);
 
 #ifdef __cplusplus
 }

@@ -41,6 +41,10 @@ def run(n, dim, nq, k, store, cluster):
     if hp[2]:
         print(f"   floor helper: {hp[0] / hp[2]:.1f} rounds per CTA, {hp[1] / max(hp[0], 1):.0f} cycles per round, first floor stored at cycle "
               f"{hp[3] / max(hp[4], 1):.0f} ({hp[4]} of {hp[2]} helpers stored one)", flush=True)
+    thr = cnt * 128.0                     # epilogue threads (issuers x 128 query rows)
+    if hp[6]:
+        print(f"   insert path per epilogue thread: {hp[5] / thr:.1f} inserts, {hp[6] / thr:.1f} slabs took the insert path "
+              f"(first 8 tiles after the warm-up: {(hp[7] >> 32) / thr:.1f} inserts, {(hp[7] & 0xFFFFFFFF) / thr:.1f} slabs)", flush=True)
     print("   progress (tile index: cycles since CTA start when the issuer begins it):", curve, "end:", round(buf[23] / max(cnt, 1)), flush=True)
     ix.close()
 
