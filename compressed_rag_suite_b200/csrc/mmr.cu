@@ -85,7 +85,7 @@ __device__ __forceinline__ float raw_to_similarity(const void* raw, size_t i, fl
     else return (float)__ddiv_rn((double)reinterpret_cast<const int32_t*>(raw)[i], (double)dim);
 }
 __device__ __forceinline__ double reference_relevance(float sim) {
-    double d = __dsub_rn(1.0, (double)sim);
+    double d = (double)__fsub_rn(1.0f, sim);        // Chroma's distance is a float32 (1.0f - cos), widened by Python
     d = fmax(0.0, fmin(2.0, d));
     const double s = __dsub_rn(1.0, __ddiv_rn(__dmul_rn(d, d), 2.0));
     return fmax(0.0, fmin(1.0, s));

@@ -247,7 +247,11 @@ class ShardIndex:
         is in use (the captured launches hold its row count and buffer addresses)."""
         import torch
         dev = torch.device("cuda", self.device)
-        q = torch.zeros((nq, self.dim), dtype=torch.float32, device=dev)
+        # warm-up / capture queries: random, NOT zeros (an all-zero query ties every row, which sends every query
+        # through the exhaustive fallback: seconds of warm-up on a large shard)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(7)
+        q = torch.randn((nq, self.dim), dtype=torch.float32, device=dev, generator=gen)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):                      # warm-up: sizes every scratch buffer the search needs

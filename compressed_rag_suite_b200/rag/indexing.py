@@ -14,7 +14,12 @@ returns ``ids / documents / metadatas / distances`` as lists of one list in asce
 Chroma distance; every failure is logged and re-raised (:121-123, :178-180).
 
 Optional additive keys (defaults reproduce the reference): ``dtype`` (f16 | bf16 | i8 |
-b1, default f16), ``device`` (CUDA ordinal, default 0).
+b1, default f16), ``device`` (CUDA ordinal, default 0), ``devices`` (list of CUDA ordinals: the
+collection is dealt out over these GPUs and searched on all of them from this one process, see
+multi.MultiDeviceIndex).  ``embeddings`` / ``query_embedding`` may be torch CUDA tensors
+(``SentenceTransformer.encode(convert_to_tensor=True)``, reference rag/embedding.py:65-71): they reach
+the ingest / search kernels without a host round trip.  One search returns at most 112 (f16 / bf16) or
+128 (i8 / b1) candidates (``collection.MAX_RESULTS``); more raises ``ValueError``.
 """
 from __future__ import annotations
 
@@ -35,13 +40,15 @@ class VectorStore:
         self.collection_name = config.get("collection_name", "rag_documents")
         self.persist_directory = config.get("persist_directory", None)
         dtype = config.get("dtype", _backend.DEFAULT_DTYPE)
-        device = config.get("device", _backend.DEFAULT_DEVICE)
+        devices = config.get("devices", None)
+        device = config.get("device", devices[0] if devices else _backend.DEFAULT_DEVICE)
         try:
             if self.persist_directory:
-                self.client = _backend.PersistentClient(path=self.persist_directory, dtype=dtype, device=device)
+                self.client = _backend.PersistentClient(path=self.persist_directory, dtype=dtype, device=device, devices=devices)
                 logger.info(f"Using persistent storage: {self.persist_directory}")
             else:
-                self.client = _backend.Client(_backend.Settings(anonymized_telemetry=False), dtype=dtype, device=device)
+                self.client = _backend.Client(_backend.Settings(anonymized_telemetry=False), dtype=dtype, device=device,
+                                              devices=devices)
                 logger.info("Using in-memory storage")
         except Exception as e:
             logger.error(f"Failed to initialize vector store client: {e}")
@@ -52,9 +59,14 @@ class VectorStore:
     def _initialize_collection(self):
         try:
             self.collection = self.client.get_collection(self.collection_name)
-        except Exception:
+        except _backend.CollectionNotFound:
             logger.info(f"Collection '{self.collection_name}' will be created on first add")
             return
+        except Exception as e:
+            # the reference treats every failure here as "no collection yet" (rag/indexing.py:53-55); a store that
+            # EXISTS but cannot be read must not be silently replaced by an empty one
+            logger.error(f"Collection '{self.collection_name}' exists but cannot be loaded: {e}")
+            raise
         logger.info(f"Loaded existing collection: {self.collection_name}")
         logger.info(f"Collection size: {self.collection.count()}")
 
@@ -86,8 +98,10 @@ class VectorStore:
         fields = _META_DEFAULT if metadata_fields is None else metadata_fields
         try:
             logger.info(f"Adding {len(chunks)} chunks to index...")
+            on_device = type(embeddings).__module__.startswith("torch") and getattr(embeddings, "is_cuda", False)
             self.collection.add(ids=[c.chunk_id for c in chunks],
-                                embeddings=np.asarray(embeddings, dtype=np.float32),   # no .tolist() boxing
+                                # no .tolist() boxing; a CUDA tensor from the embedder stays on the device
+                                embeddings=embeddings if on_device else np.asarray(embeddings, dtype=np.float32),
                                 documents=[c.text for c in chunks],
                                 metadatas=[self._chunk_metadata(c, fields) for c in chunks])
             logger.info(f"Index created successfully! Total documents: {self.collection.count()}")
@@ -106,13 +120,21 @@ class VectorStore:
             logger.warning("Collection is empty. No results to return.")
             return {"ids": [[]], "documents": [[]], "metadatas": [[]], "distances": [[]]}
         top_k = min(top_k, size)
+        # the reference's conversion (:156-168): an ndarray of any shape is ONE query (flattened); a list whose first
+        # element is a list is passed through as a batch of queries; anything else is one query
         if isinstance(query_embedding, np.ndarray):
-            vec = query_embedding.reshape(-1)
+            batch = query_embedding.reshape(1, -1)
+        elif type(query_embedding).__module__.startswith("torch") and getattr(query_embedding, "is_cuda", False):
+            batch = query_embedding.reshape(1, -1)                    # stays on the device
         else:
-            vec = np.asarray(list(query_embedding), dtype=np.float32).reshape(-1)
+            as_list = query_embedding if isinstance(query_embedding, list) else list(query_embedding)
+            if len(as_list) and isinstance(as_list[0], list):
+                batch = np.asarray(as_list, dtype=np.float32)
+            else:
+                batch = np.asarray(as_list, dtype=np.float32).reshape(1, -1)
         try:
             extra = {} if min_similarity is None else {"min_similarity": float(min_similarity)}
-            return self.collection.query(query_embeddings=vec[None, :], n_results=top_k,
+            return self.collection.query(query_embeddings=batch, n_results=top_k,
                                          where=where, where_document=where_document, **extra)
         except Exception as e:
             logger.error(f"Search failed: {e}")

@@ -128,7 +128,9 @@ class ContextRetriever:
         if not queries:
             return []
         try:
-            emb = np.asarray(self.embedding_model.embed(list(queries)), dtype=np.float32)
+            emb = self.embedding_model.embed(list(queries))
+            if not (type(emb).__module__.startswith("torch") and getattr(emb, "is_cuda", False)):
+                emb = np.asarray(emb, dtype=np.float32)               # a CUDA tensor from the embedder stays on the device
             col = self.vector_store.collection
             if col is None:
                 raise ValueError("No collection available. Create index first.")

@@ -222,7 +222,9 @@ class ShardedSearcher:
             raise ValueError("capture needs the peer exchange")
         ix = self.index
         dev = torch.device("cuda", ix.device)
-        q = torch.zeros((nq, ix.dim), dtype=torch.float32, device=dev)
+        gen = torch.Generator(device=dev)                  # random warm-up queries, the same on every rank (see capture_search)
+        gen.manual_seed(7)
+        q = torch.randn((nq, ix.dim), dtype=torch.float32, device=dev, generator=gen)
         ex = self._peer_exchange(nq, k) if self.world > 1 else None
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -254,10 +256,10 @@ def assemble_over_shards(t, group=None):
 
 def reference_relevance(sims):
     """The reference's `score` of a hit from its cosine similarity, in float64 exactly as Python
-    evaluates it: Chroma distance d = 1 - cos (rag/indexing.py:171-176), then
+    evaluates it: Chroma distance d = float32(1 - cos) (rag/indexing.py:171-176), then
     rag/retrieval.py:75-77: d <- clamp(d, 0, 2); score = clamp(1 - d*d/2, 0, 1)."""
     import torch
-    d = 1.0 - sims.to(torch.float64)
+    d = (1.0 - sims.to(torch.float32)).to(torch.float64)
     d = torch.clamp(d, 0.0, 2.0)
     return torch.clamp(1.0 - (d * d / 2.0), 0.0, 1.0)
 

@@ -161,7 +161,8 @@ class Collection:
             raw = _srch.raw_scores(codes, qc, prec, dim)
             sims = _srch.similarity_from_raw(raw, prec, dim)
             self._last_raw = raw
-        return 1.0 - sims.astype(np.float64)      # same expression as the product host code
+        # Chroma (hnswlib) computes the distance in float32 (1.0f - dot) and hands that float32 to Python
+        return (np.float32(1.0) - sims.astype(np.float32)).astype(np.float64)
 
     def query(self, query_embeddings, n_results=10, where=None, where_document=None,
               include=None) -> Dict[str, Any]:

@@ -38,7 +38,7 @@ def search_then_mmr(x, q, store, k, fetch_k, diversity_penalty, min_similarity=-
             continue
         cid = ids[i, :c].astype(np.int64)
         sims = search.similarity_from_raw(raw[i, :c], store, dim)
-        rel = [postprocess.distance_to_similarity(1.0 - float(s)) for s in sims]
+        rel = [postprocess.distance_to_similarity(float(np.float32(1.0) - np.float32(s))) for s in sims]
         dec = decode_rows(codes[cid], store)
         if store == "b1":
             dec = dec[:, :dim]

@@ -202,3 +202,180 @@ def test_plain_c_host_runs_a_search(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
     assert "rank 0: row 123" in r.stdout
+
+
+# ---------------------------------------------------------------- round 2: devices, device tensors, append-only persistence
+def _texts_chunks(n):
+    texts = [f"{'alpha' if i % 3 else 'omega'} body text {i}" for i in range(n)]
+    chunks = [Chunk(t, f"chunk_{i}", 0, len(t), page_number=i % 11, section=f"s{i % 4}" if i % 5 else None)
+              for i, t in enumerate(texts)]
+    return texts, chunks
+
+
+@pytest.mark.parametrize("dtype", ["f16", "i8"])
+@pytest.mark.parametrize("devices", [[0, 0], [0, 0, 0]])
+def test_vectorstore_over_several_devices_equals_one_device(dtype, devices, tmp_path):
+    """``devices``: the collection is dealt out over several shards (here: side by side on the one GPU of the
+    box) and every search runs on all of them from this one process — push to the peers' receive buffers,
+    one merge.  Same dicts as the single-device store (rag/indexing.py:125-180 contract), with duplicates
+    (ties -> first inserted row ACROSS shards), incremental adds, filters, MMR and a reload."""
+    rng = np.random.default_rng(31)
+    n, dim = 1500, 384
+    x = rng.standard_normal((n, dim)).astype(np.float32)
+    x[900] = x[3]
+    x[1400] = x[3]                                       # equal rows on different shards
+    texts, chunks = _texts_chunks(n)
+    one = VectorStore({"collection_name": "one", "dtype": dtype})
+    many = VectorStore({"collection_name": "many", "dtype": dtype, "devices": devices,
+                        "persist_directory": str(tmp_path / "db")})
+    for lo, hi in [(0, 700), (700, 701), (701, 703), (703, n)]:          # bulk, single-row and short adds
+        one.create_index(chunks[lo:hi], x[lo:hi])
+        many.create_index(chunks[lo:hi], x[lo:hi])
+    assert many.get_stats()["count"] == n
+    qs = [x[3], x[77] + 0.05 * rng.standard_normal(dim).astype(np.float32), rng.standard_normal(dim).astype(np.float32)]
+    for q in qs:
+        for where, where_doc in [(None, None), ({"page_number": {"$gte": 6}}, None), (None, {"$contains": "omega"})]:
+            a = one.search(q, top_k=9, where=where, where_document=where_doc)
+            b = many.search(q, top_k=9, where=where, where_document=where_doc)
+            assert a == b, (where, where_doc)
+    assert many.search(x[3], top_k=3)["ids"] == [["chunk_3", "chunk_900", "chunk_1400"]]
+    emb = TableEmbedder()
+    emb.table["q0"], emb.table["q1"] = qs[1], qs[2]
+    cfg = {"top_k": 4, "rerank": True, "diversity_penalty": 0.2, "similarity_threshold": 0.1}
+    ra, rb = ContextRetriever(one, emb, cfg), ContextRetriever(many, emb, cfg)
+    assert ra.retrieve("q0") == rb.retrieve("q0")
+    assert ra.retrieve_batch(["q0", "q1"]) == rb.retrieve_batch(["q0", "q1"])
+    assert not any(t for t, _ in many.collection.index.exchange_status())
+    again = VectorStore({"collection_name": "many", "dtype": dtype, "devices": devices,
+                         "persist_directory": str(tmp_path / "db")})
+    assert again.get_stats()["count"] == n
+    for q in qs:
+        assert again.search(q, top_k=9) == one.search(q, top_k=9)
+
+
+def test_device_tensors_from_the_embedder_never_touch_the_host():
+    """N4: ``SentenceTransformer.encode(convert_to_tensor=True)`` hands CUDA tensors to create_index / search /
+    retrieve_batch (reference rag/embedding.py:65-71, rag/indexing.py:116): same results as numpy input."""
+    import torch
+    rng = np.random.default_rng(32)
+    n, dim = 3000, 384
+    x = rng.standard_normal((n, dim)).astype(np.float32)
+    texts, chunks = _texts_chunks(n)
+    host = VectorStore({"collection_name": "host"})
+    host.create_index(chunks, x)
+    devs = VectorStore({"collection_name": "dev"})
+    xd = torch.from_numpy(x).cuda()
+    devs.create_index(chunks[:2000], xd[:2000])
+    devs.create_index(chunks[1990:], xd[1990:])          # 10 ids already present: dropped on the device
+    assert devs.get_stats()["count"] == n
+    q = rng.standard_normal((5, dim)).astype(np.float32)
+    for i in range(5):
+        assert devs.search(torch.from_numpy(q[i]).cuda(), top_k=7) == host.search(q[i], top_k=7)
+        assert devs.search(torch.from_numpy(q[i]).cuda(), top_k=7, where={"page_number": 4}) == \
+            host.search(q[i], top_k=7, where={"page_number": 4})
+
+    class CudaEmbedder:
+        def embed(self, texts):
+            if isinstance(texts, str):
+                return torch.from_numpy(q[int(texts[1:])]).cuda()
+            return torch.from_numpy(np.stack([q[int(t[1:])] for t in texts])).cuda()
+
+    class HostEmbedder:
+        def embed(self, texts):
+            if isinstance(texts, str):
+                return q[int(texts[1:])]
+            return np.stack([q[int(t[1:])] for t in texts])
+
+    cfg = {"top_k": 3, "rerank": True, "diversity_penalty": 0.1}
+    a = ContextRetriever(devs, CudaEmbedder(), cfg)
+    b = ContextRetriever(host, HostEmbedder(), cfg)
+    names = [f"q{i}" for i in range(5)]
+    assert a.retrieve_batch(names) == b.retrieve_batch(names)
+    assert [a.retrieve(t) for t in names] == [b.retrieve(t) for t in names]
+
+
+def test_search_input_forms_follow_the_reference():
+    """rag/indexing.py:156-168: an ndarray of any shape is ONE query; a list of lists is a batch."""
+    x = np.eye(8, dtype=np.float32)
+    chunks = [Chunk(f"d{i}", f"chunk_{i}", 0, 2) for i in range(8)]
+    vs = VectorStore({"collection_name": "forms"})
+    vs.create_index(chunks, x)
+    assert vs.search(x[2].reshape(1, 8), top_k=1)["ids"] == [["chunk_2"]]
+    assert vs.search(x[2].reshape(2, 4), top_k=1)["ids"] == [["chunk_2"]]           # flattened, as the reference does
+    assert vs.search(iter(x[5].tolist()), top_k=1)["ids"] == [["chunk_5"]]
+    out = vs.search([x[1].tolist(), x[6].tolist()], top_k=2)                        # list of lists: two queries
+    assert [r[0] for r in out["ids"]] == ["chunk_1", "chunk_6"] and len(out["distances"]) == 2
+    d = vs.search(x[0], top_k=8)["distances"][0]
+    assert all(v == float(np.float32(v)) for v in d)                                # float32 distances, like Chroma
+    with pytest.raises(ValueError):
+        vs.search(np.zeros(7, np.float32), top_k=1)
+
+
+def test_more_candidates_than_a_search_returns_is_a_clear_error():
+    rng = np.random.default_rng(33)
+    x = rng.standard_normal((400, 64)).astype(np.float32)
+    chunks = [Chunk(f"d{i}", f"chunk_{i}", 0, 2) for i in range(400)]
+    vs = VectorStore({"collection_name": "caps"})
+    vs.create_index(chunks, x)
+    assert len(vs.search(x[0], top_k=112)["ids"][0]) == 112
+    with pytest.raises(ValueError, match="exceeds"):
+        vs.search(x[0], top_k=113)
+    r = ContextRetriever(vs, TableEmbedder(), {"top_k": 60, "rerank": True})
+    r.embedding_model.table["q"] = x[0]
+    with pytest.raises(ValueError, match="exceeds"):
+        r.retrieve("q")                                                             # fetches 2 * 60
+
+
+def test_persistence_is_append_only_and_survives_torn_writes(tmp_path):
+    from compressed_rag_suite_b200 import collection as backend
+    rng = np.random.default_rng(34)
+    n, dim = 900, 384
+    x = rng.standard_normal((n, dim)).astype(np.float32)
+    texts, chunks = _texts_chunks(n)
+    d = str(tmp_path / "db")
+    cfg = {"collection_name": "col", "persist_directory": d}
+    a = VectorStore(cfg)
+    sizes = []
+    for lo, hi in [(0, 300), (300, 301), (301, 900)]:
+        a.create_index(chunks[lo:hi], x[lo:hi])
+        sizes.append((os.path.getsize(os.path.join(d, "col.crs")), os.path.getsize(os.path.join(d, "col.rows.jsonl"))))
+    assert [s[0] for s in sizes] == [64 + 300 * 768, 64 + 301 * 768, 64 + 900 * 768]       # the blob only ever grows by the new rows
+    assert sizes[0][1] < sizes[1][1] < sizes[2][1]
+    assert not [f for f in os.listdir(d) if f.endswith(".tmp")]
+    want = a.search(x[5], top_k=6)
+    # (1) a crash in the middle of appending a sidecar line, and garbage behind the last complete row of the blob
+    with open(os.path.join(d, "col.rows.jsonl"), "ab") as f:
+        f.write(b'["chunk_900", "torn li')
+    with open(os.path.join(d, "col.crs"), "ab") as f:
+        f.write(b"\x01" * 100)
+    b = VectorStore(cfg)
+    assert b.get_stats()["count"] == n and b.search(x[5], top_k=6) == want
+    extra = [Chunk("late", "chunk_late", 0, 4, page_number=1)]
+    b.create_index(extra, x[:1] * -1.0)                                  # appending after the repair works
+    assert VectorStore(cfg).get_stats()["count"] == n + 1
+    # (2) the sidecar lost its last rows (the blob was flushed, the lines were not): the common prefix is kept
+    lines = open(os.path.join(d, "col.rows.jsonl"), "rb").read().splitlines(keepends=True)
+    with open(os.path.join(d, "col.rows.jsonl"), "wb") as f:
+        f.writelines(lines[:850])
+    c = VectorStore(cfg)
+    assert c.get_stats()["count"] == 850
+    assert c.search(x[880], top_k=1)["ids"] != [["chunk_880"]]
+    c.create_index(chunks[850:], x[850:])
+    assert c.get_stats()["count"] == n and c.search(x[880], top_k=1)["ids"] == [["chunk_880"]]
+    assert c.search(x[5], top_k=6) == want
+    assert VectorStore(cfg).search(x[5], top_k=6) == want
+    # (3) a header that lies about the row count is clamped to the rows present; a corrupt one is an error, not an empty store
+    import struct
+    blob = os.path.join(d, "col.crs")
+    raw = bytearray(open(blob, "rb").read())
+    struct.pack_into("<q", raw, 24, 10 ** 12)
+    open(blob, "wb").write(bytes(raw))
+    assert VectorStore(cfg).get_stats()["count"] == n
+    struct.pack_into("<q", raw, 24, -5)
+    open(blob, "wb").write(bytes(raw))
+    with pytest.raises(backend.CorruptStoreError):
+        VectorStore(cfg)
+    # (4) a ChromaDB directory is not readable: the store starts empty (and logs why)
+    os.makedirs(str(tmp_path / "chroma"), exist_ok=True)
+    open(str(tmp_path / "chroma" / "chroma.sqlite3"), "wb").close()
+    assert VectorStore({"collection_name": "col", "persist_directory": str(tmp_path / "chroma")}).collection is None

@@ -122,7 +122,7 @@ def _worker_stages(rank, world, port, out_dir):
         # --- relevance transform equals the reference's Python arithmetic
         sims = search.similarity_from_raw(m_raw, "i8", dim)
         rel = reference_relevance(torch.from_numpy(sims)).numpy()
-        want_rel = [[postprocess.distance_to_similarity(1.0 - float(s)) for s in row] for row in sims]
+        want_rel = [[postprocess.distance_to_similarity(float(np.float32(1.0) - np.float32(s))) for s in row] for row in sims]
         assert rel.tolist() == want_rel
         np.savez(os.path.join(out_dir, f"stages{rank}.npz"), ids=m_ids, fine=fine_t.numpy())
     finally:
