@@ -60,6 +60,11 @@ SYMBOLS = {
     "crs_index_search_push": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_float, _P]),
     "crs_index_map_ids": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_uint32]),
     "crs_exchange_merge": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "crs_index_codes_handle": (C.c_int, [_P, _P, C.POINTER(_P), C.POINTER(C.c_uint32), C.POINTER(C.c_int64)]),
+    "crs_exchange_open_shards": (C.c_int, [_P, _P, _P, C.POINTER(C.c_uint32), C.POINTER(C.c_int64)]),
+    "crs_exchange_set_shards": (C.c_int, [_P, _P, C.POINTER(_P), C.POINTER(C.c_uint32), C.POINTER(C.c_int64)]),
+    "crs_exchange_fetch_rows": (C.c_int, [_P, _P, _P, C.c_int, _P]),
+    "crs_exchange_score_rows": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_int, _P]),
     "crs_index_save": (C.c_int, [_P, C.c_char_p]),
     "crs_index_append": (C.c_int, [_P, C.c_char_p]),
     "crs_index_truncate": (C.c_int, [_P, C.c_int64]),

@@ -115,6 +115,7 @@ struct crs_index {
     int64_t sample_rows = 0;    // rows of an optional sample pass that seeds the contraction's per-query floors (0 = off)
     int share_floor = 1;        // contraction: the slices of a query share their k-th best score while the launch runs
     int gemm_warm = 8;          // contraction: first tiles of every slice that only seed the floor and are redone last
+    int fuse_encode = 1;        // single-query scans encode the query in their own prologue (no separate encode launch)
     int short_lists = 1;        // integer scans with k > 32 keep 32 keys per CTA + certification (0 = full 128-key lists)
     int multi_scan = 8;         // largest group of short-row integer queries that shares one corpus pass (<= 1: off)
     int gemm_min_nq = 2;        // batches of at least this many queries take the tensor-core path: one corpus read for
@@ -149,6 +150,9 @@ struct crs_exchange {
     void* peers[crs::kMaxWorld] = {};              // every rank's receive buffer as seen from this device (own = buf)
     bool ipc_opened[crs::kMaxWorld] = {};
     bool wired = false;
+    crs::PeerShards shards{};                      // every rank's stored rows (crs_exchange_open_shards), world = 0: none
+    bool shard_ipc[crs::kMaxWorld] = {};
+    DevScratch<uint8_t> gather;                    // candidate rows fetched for crs_exchange_score_rows
 };
 
 namespace {
@@ -319,6 +323,7 @@ int crs_index_set_option(crs_index* ix, const char* name, int64_t value) {
     else if (!strcmp(name, "short_lists")) ix->short_lists = (int)value;
     else if (!strcmp(name, "sample_rows")) ix->sample_rows = value;
     else if (!strcmp(name, "share_floor")) ix->share_floor = (int)value;
+    else if (!strcmp(name, "fuse_encode")) ix->fuse_encode = (int)value;
     else if (!strcmp(name, "gemm_warm")) ix->gemm_warm = (int)std::max<int64_t>(0, std::min<int64_t>(value, 64));
     else if (!strcmp(name, "eps_scale")) ix->eps_scale = (double)value / 1000.0;
     else if (!strcmp(name, "profiling")) {
@@ -558,15 +563,24 @@ static int search_impl(crs_index* ix, const void* queries, int nq, int k, float 
         }
         CRS_CUDA(ix->qcodes.ensure((size_t)nq * ix->row_bytes));
         CRS_CUDA(ix->qnorms.ensure((size_t)nq));
-        CRS_CUDA(crs::launch_encode(st, qd, nq, ix->dim, ix->dim_padded, ix->store, ix->metric, ix->i8_scale,
-                                    ix->qcodes.p, ix->qnorms.p, ix->n_flagged /*reset "uncertified this search"*/,
-                                    ex ? ex->ctl : nullptr /*advance the exchange's step stamp*/));
-        ++launches;
-
         // ---- plan: persistent grid, one candidate list per CTA
         crs::ScanPlan plan;
         plan.lpl = lpl;
         plan.grid = ix->num_sms;
+        // a single-query scan encodes the query in its own prologue; everything else gets an encode launch
+        const bool fused_q = !use_gemm && nq == 1 && ix->fuse_encode != 0 && ix->dim <= 2048 &&
+                             !(is_float && ix->force_exact != 0);
+        if (fused_q) {
+            plan.fq.src = qd; plan.fq.dim = ix->dim; plan.fq.cosine = ix->metric == CRS_COSINE;
+            plan.fq.i8_mult = 127.0 / (double)ix->i8_scale;
+            plan.fq.qcodes_out = ix->qcodes.p; plan.fq.qnorm_out = ix->qnorms.p;
+            plan.fq.zero_word = ix->n_flagged; plan.fq.inc_word = ex ? ex->ctl : nullptr;
+        } else {
+            CRS_CUDA(crs::launch_encode(st, qd, nq, ix->dim, ix->dim_padded, ix->store, ix->metric, ix->i8_scale,
+                                        ix->qcodes.p, ix->qnorms.p, ix->n_flagged /*reset "uncertified this search"*/,
+                                        ex ? ex->ctl : nullptr /*advance the exchange's step stamp*/));
+            ++launches;
+        }
         if (allow_bits) {                       // row bitmap of a where / where_document filter
             const size_t words = (size_t)((ix->count + 31) / 32);
             if (is_device_ptr(allow_bits)) {
@@ -993,8 +1007,11 @@ int crs_exchange_destroy(crs_exchange* ex) {
     {
         DeviceGuard g(ex->device);
         cudaDeviceSynchronize();
-        for (int r = 0; r < ex->world; ++r)
+        for (int r = 0; r < ex->world; ++r) {
             if (ex->ipc_opened[r] && ex->peers[r]) cudaIpcCloseMemHandle(ex->peers[r]);
+            if (ex->shard_ipc[r] && ex->shards.codes[r]) cudaIpcCloseMemHandle(const_cast<uint8_t*>(ex->shards.codes[r]));
+        }
+        ex->gather.release();
         if (ex->buf) cudaFree(ex->buf);
         if (ex->ctl) cudaFree(ex->ctl);
         if (ex->local) cudaFree(ex->local);
@@ -1068,6 +1085,108 @@ int crs_exchange_status(crs_exchange* ex, void* cuda_stream, int* timed_out, uin
     CRS_CUDA(cudaStreamSynchronize(st));
     if (step) *step = w[0];
     if (timed_out) *timed_out = (int)w[1];
+    return CRS_OK;
+}
+
+// ---- peer access to the shards' stored rows (candidate vectors for MMR / rescoring without a second collective)
+int crs_index_codes_handle(crs_index* ix, void* out_handle64, void** out_ptr, uint32_t* row_base, int64_t* count) {
+    if (!ix) return fail(CRS_EINVAL, "index is NULL");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    if (out_handle64) {
+        if (!ix->codes) return fail(CRS_ESTATE, "the index holds no rows yet");
+        cudaIpcMemHandle_t h;
+        CRS_CUDA(cudaIpcGetMemHandle(&h, ix->codes));
+        memcpy(out_handle64, &h, sizeof(h));
+    }
+    if (out_ptr) *out_ptr = ix->codes;
+    if (row_base) *row_base = ix->row_base;
+    if (count) *count = ix->count;
+    return CRS_OK;
+}
+
+static int set_shards(crs_exchange* ex, crs_index* own, const void* handles, void* const* ptrs,
+                      const uint32_t* row_bases, const int64_t* counts) {
+    if (!ex || !own || !row_bases || !counts || (!handles && !ptrs)) return fail(CRS_EINVAL, "bad argument");
+    if (own->device != ex->device) return fail(CRS_EINVAL, "exchange and index live on different devices");
+    DeviceGuard g(ex->device);
+    for (int r = 0; r < ex->world; ++r) {
+        if (ex->shard_ipc[r] && ex->shards.codes[r]) cudaIpcCloseMemHandle(const_cast<uint8_t*>(ex->shards.codes[r]));
+        ex->shard_ipc[r] = false;
+        ex->shards.codes[r] = nullptr;
+    }
+    for (int r = 0; r < ex->world; ++r) {
+        ex->shards.row_base[r] = row_bases[r];
+        ex->shards.count[r] = counts[r];
+        if (r == ex->rank) { ex->shards.codes[r] = own->codes; continue; }
+        if (counts[r] == 0) continue;
+        if (handles) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, reinterpret_cast<const uint8_t*>(handles) + (size_t)r * sizeof(h), sizeof(h));
+            void* p = nullptr;
+            CRS_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            ex->shards.codes[r] = reinterpret_cast<const uint8_t*>(p);
+            ex->shard_ipc[r] = true;
+        } else {
+            cudaPointerAttributes a;
+            CRS_CUDA(cudaPointerGetAttributes(&a, ptrs[r]));
+            if (a.type != cudaMemoryTypeDevice) return fail(CRS_EINVAL, "shard pointer is not device memory");
+            if (a.device != ex->device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(a.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+                cudaGetLastError();
+            }
+            ex->shards.codes[r] = reinterpret_cast<const uint8_t*>(ptrs[r]);
+        }
+    }
+    ex->shards.world = ex->world;
+    ex->shards.row_bytes = (int)own->row_bytes;
+    return CRS_OK;
+}
+
+int crs_exchange_open_shards(crs_exchange* ex, crs_index* own, const void* handles, const uint32_t* row_bases,
+                             const int64_t* counts) {
+    return set_shards(ex, own, handles, nullptr, row_bases, counts);
+}
+
+int crs_exchange_set_shards(crs_exchange* ex, crs_index* own, void* const* codes_ptrs, const uint32_t* row_bases,
+                            const int64_t* counts) {
+    return set_shards(ex, own, nullptr, codes_ptrs, row_bases, counts);
+}
+
+int crs_exchange_fetch_rows(crs_exchange* ex, void* cuda_stream, const uint32_t* ids, int n, void* out_codes) {
+    if (!ex) return fail(CRS_EINVAL, "exchange is NULL");
+    if (ex->shards.world == 0) return fail(CRS_ESTATE, "no shards registered with this exchange");
+    if (n < 0) return fail(CRS_EINVAL, "n must be >= 0");
+    if (n == 0) return CRS_OK;
+    if (!is_device_ptr(ids) || !is_device_ptr(out_codes)) return fail(CRS_EINVAL, "crs_exchange_fetch_rows takes device buffers");
+    DeviceGuard g(ex->device);
+    CRS_CUDA(crs::launch_peer_gather(reinterpret_cast<cudaStream_t>(cuda_stream), ex->shards, ids, n, out_codes));
+    return CRS_OK;
+}
+
+int crs_exchange_score_rows(crs_index* ix, crs_exchange* ex, const void* queries, int nq, const uint32_t* ids, int m,
+                            void* out_scores) {
+    if (!ix || !ex) return fail(CRS_EINVAL, "bad argument");
+    if (ex->shards.world == 0) return fail(CRS_ESTATE, "no shards registered with this exchange");
+    if (nq < 0 || m < 0) return fail(CRS_EINVAL, "nq and m must be >= 0");
+    if (nq == 0 || m == 0) return CRS_OK;
+    if (!is_device_ptr(queries) || !is_device_ptr(ids) || !is_device_ptr(out_scores))
+        return fail(CRS_EINVAL, "crs_exchange_score_rows takes device buffers");
+    if ((int)ix->row_bytes != ex->shards.row_bytes) return fail(CRS_EINVAL, "index and registered shards differ in row width");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = ix->stream;
+    const size_t total = (size_t)nq * m;
+    CRS_CUDA(ix->qcodes.ensure((size_t)nq * ix->row_bytes));
+    CRS_CUDA(ix->qnorms.ensure((size_t)nq));
+    CRS_CUDA(crs::launch_encode(st, reinterpret_cast<const float*>(queries), nq, ix->dim, ix->dim_padded, ix->store, ix->metric,
+                                ix->i8_scale, ix->qcodes.p, ix->qnorms.p));
+    CRS_CUDA(ex->gather.ensure(total * ix->row_bytes));
+    CRS_CUDA(crs::launch_peer_gather(st, ex->shards, ids, (int)total, ex->gather.p));
+    // pair i scores gathered row i (ids = NULL form of K8); pad ids were gathered as zero rows and are masked by the caller
+    CRS_CUDA(crs::launch_score_rows(st, ex->gather.p, (int64_t)total, 0, (int)ix->row_bytes, ix->dim, ix->store,
+                                    ix->qcodes.p, nullptr, nq, m, out_scores));
     return CRS_OK;
 }
 

@@ -9,10 +9,26 @@ namespace crs {
 // Widest candidate list a search keeps per query: M = 32 * LPL keys, LPL in {1, 4}.
 constexpr int kMaxListLen = 128;
 
+// Optional: a single-query scan encodes the fp32 query ITSELF in its prologue (every CTA redundantly, in shared
+// memory, while its producer warp already streams the first tiles), instead of a separate encode launch in
+// front of it — the launch and its gap were ~10 us of a 150 us single-query search.  Same arithmetic as
+// ingest.cu (oracle/encode.py).  CTA 0 also stores the codes / norm bound for finalize.
+struct FusedQuery {
+    const float* src = nullptr;        // [dim] fp32 on the device; NULL = the query arrives encoded (qcodes)
+    int dim = 0;
+    int cosine = 0;
+    double i8_mult = 127.0;
+    void* qcodes_out = nullptr;        // [row_bytes]
+    float* qnorm_out = nullptr;        // [1]
+    int32_t* zero_word = nullptr;      // the counters the encode kernel resets / advances
+    uint32_t* inc_word = nullptr;
+};
+
 struct ScanPlan {
     int grid;          // persistent CTAs
     int lpl;           // list entries per lane (1 -> M = 32, 4 -> M = 128)
     const uint32_t* allow = nullptr;   // optional row bitmap (bit r%32 of word r/32): metadata / document filter
+    FusedQuery fq;                     // optional fused query encode (single-query scans)
 };
 
 // K0: fp32 rows -> stored codes (normalise for cosine, cast / quantise / sign-pack).
@@ -143,6 +159,15 @@ struct XchgArgs {
 };
 int xmerge_ctas(int nq);
 cudaError_t launch_xmerge(cudaStream_t st, const XchgArgs& a);
+// every rank's stored rows as seen from this device (peer-mapped): rank r holds global ids [row_base[r], row_base[r] + count[r])
+struct PeerShards {
+    const uint8_t* codes[kMaxWorld];
+    uint32_t row_base[kMaxWorld];
+    int64_t count[kMaxWorld];
+    int world;
+    int row_bytes;
+};
+cudaError_t launch_peer_gather(cudaStream_t st, const PeerShards& sh, const uint32_t* ids, int n, void* out);
 
 // K6: greedy MMR over m candidate vectors per query.  `fused` (optional): take the search output instead of
 // a relevance array and emit the selected hits (ids / similarity / reference score) directly.

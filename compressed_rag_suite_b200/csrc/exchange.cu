@@ -135,6 +135,35 @@ xmerge_kernel(XchgArgs a) {
     if (lane == 0) a.out_counts[q] = count;
 }
 
+// ---- candidate rows by global id, read straight out of the owning shard's HBM over NVLink peer memory
+// (replaces the MAX all-reduce that used to assemble [nq, m, row_bytes] candidate codes on every rank).
+// One CTA per id; rows no shard owns (pad ids) are zero-filled.
+__global__ void __launch_bounds__(64)
+peer_gather_kernel(PeerShards sh, const uint32_t* __restrict__ ids, int n, uint4* __restrict__ out) {
+    const int i = blockIdx.x;
+    if (i >= n) return;
+    const uint32_t gid = ids[i];
+    const int chunks = sh.row_bytes / 16;
+    const uint4* src = nullptr;
+    if (gid != CRS_PAD_ID) {
+        for (int r = 0; r < sh.world; ++r) {
+            const int64_t local = (int64_t)gid - (int64_t)sh.row_base[r];
+            if (local >= 0 && local < sh.count[r]) {
+                src = reinterpret_cast<const uint4*>(sh.codes[r]) + local * chunks;
+                break;
+            }
+        }
+    }
+    for (int c = threadIdx.x; c < chunks; c += blockDim.x)
+        out[(int64_t)i * chunks + c] = src ? src[c] : make_uint4(0u, 0u, 0u, 0u);
+}
+
+cudaError_t launch_peer_gather(cudaStream_t st, const PeerShards& sh, const uint32_t* ids, int n, void* out) {
+    if (n <= 0) return cudaSuccess;
+    peer_gather_kernel<<<n, 64, 0, st>>>(sh, ids, n, reinterpret_cast<uint4*>(out));
+    return cudaGetLastError();
+}
+
 int xmerge_ctas(int nq) { return (nq + kXWarps - 1) / kXWarps; }
 
 cudaError_t launch_xmerge(cudaStream_t st, const XchgArgs& a) {

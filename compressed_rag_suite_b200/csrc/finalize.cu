@@ -120,13 +120,21 @@ finalize_kernel(FinalizeArgs a) {
         const int chunks = a.dim_padded / 8;
         const int stride16 = chunks + 1;                       // in 16-byte units
         const uint4* qglob = reinterpret_cast<const uint4*>(a.qcodes) + (size_t)q * chunks;
+        // Candidates more than 2 eps below the k-th best FAST score cannot reach the exact top-k: their exact
+        // score is below fast_k - eps, and each of the k best-by-fast rows scores at least that exactly.  (If one
+        // of those k fails the threshold, so does everything below it.)  Their rows are neither fetched nor
+        // rescored: about k + a few random row reads per query instead of M.
+        float skip_below = -INFINITY;
+        if (a.k <= M && fast_keys[a.k - 1] != 0ull)
+            skip_below = unorderable_f32(key_ord(fast_keys[a.k - 1])) - 2.0f * a.eps_rel * a.qnorms[q] * a.row_norm_bound;
         if (a.stage_rows) {
             uint4* sm = reinterpret_cast<uint4*>(rows_sm);
             for (int i = threadIdx.x; i < (M + 1) * chunks; i += blockDim.x) {
                 const int r = i / chunks, c = i - r * chunks;
                 uint4 v = make_uint4(0u, 0u, 0u, 0u);
                 if (r == M) v = qglob[c];                      // last slot: the query
-                else if (fast_keys[r] != 0ull) v = (reinterpret_cast<const uint4*>(a.codes) + (size_t)key_id(fast_keys[r]) * chunks)[c];
+                else if (fast_keys[r] != 0ull && unorderable_f32(key_ord(fast_keys[r])) >= skip_below)
+                    v = (reinterpret_cast<const uint4*>(a.codes) + (size_t)key_id(fast_keys[r]) * chunks)[c];
                 sm[(size_t)r * stride16 + c] = v;
             }
             __syncthreads();
@@ -135,7 +143,7 @@ finalize_kernel(FinalizeArgs a) {
             const uint64_t fk = fast_keys[threadIdx.x];
             uint64_t ek = 0ull;
             float err = 0.f;
-            if (fk != 0ull) {
+            if (fk != 0ull && unorderable_f32(key_ord(fk)) >= skip_below) {
                 const uint32_t id = key_id(fk);
                 const uint4* row = a.stage_rows ? reinterpret_cast<const uint4*>(rows_sm) + (size_t)threadIdx.x * stride16
                                                 : reinterpret_cast<const uint4*>(a.codes) + (size_t)id * chunks;

@@ -45,12 +45,68 @@ __device__ __forceinline__ float2 cvt_pair(uint32_t v) {
     }
 }
 
+// Fused query encode (see FusedQuery): the NT consumer threads of a CTA turn the fp32 query into its stored
+// form in shared memory.  Arithmetic and order are those of ingest.cu: n2 accumulated sequentially in fp64 by
+// ONE thread, y = x / sqrt(n2) in fp64, one rounding to the store dtype.
+template <int KIND, int NT>
+__device__ __forceinline__ void encode_query_cta(const FusedQuery& fq, int dim_padded, float* qstage, uint8_t* qenc,
+                                                 int tid, bool first_cta) {
+    __shared__ double s_div;
+    __shared__ int s_zero;
+    for (int j = tid; j < fq.dim; j += NT) qstage[j] = fq.src[j];
+    named_barrier_1<NT>();
+    if (tid == 0) {
+        double n2 = 0.0;
+        for (int j0 = 0; j0 < fq.dim; j0 += 16) {                 // loads and converts run ahead of the serial FMA chain
+            double xv[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) xv[j] = (j0 + j < fq.dim) ? (double)qstage[j0 + j] : 0.0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) n2 = fma(xv[j], xv[j], n2);
+        }
+        const double norm = sqrt(n2);
+        s_div = (fq.cosine && norm > 0.0) ? norm : 1.0;
+        s_zero = (fq.cosine && !(norm > 0.0)) ? 1 : 0;
+        if (first_cta) {
+            if (fq.qnorm_out) *fq.qnorm_out = fq.cosine ? 1.00390625f : __double2float_ru(norm) * 1.00390625f;
+            if (fq.zero_word) *fq.zero_word = 0;
+            if (fq.inc_word) *fq.inc_word += 1u;
+        }
+    }
+    named_barrier_1<NT>();
+    const double dv = s_div;
+    const bool zr = s_zero != 0;
+    for (int j = tid; j < dim_padded; j += NT) {                  // NT is a multiple of 32: a warp covers 32 consecutive j
+        double y = 0.0;
+        if (j < fq.dim && !zr) y = (double)qstage[j] / dv;
+        if constexpr (KIND == kF16) {
+            reinterpret_cast<__half*>(qenc)[j] = __double2half(y);
+        } else if constexpr (KIND == kBF16) {
+            reinterpret_cast<__nv_bfloat16*>(qenc)[j] = __double2bfloat16(y);
+        } else if constexpr (KIND == kI8) {
+            double q = rint(y * fq.i8_mult);
+            q = fmin(127.0, fmax(-127.0, q));
+            reinterpret_cast<int8_t*>(qenc)[j] = (int8_t)(int)q;
+        } else {
+            const unsigned bits = __ballot_sync(CRS_FULL_MASK, y > 0.0);
+            if ((tid & 31) == 0) reinterpret_cast<uint32_t*>(qenc)[j >> 5] = bits;
+        }
+    }
+    named_barrier_1<NT>();
+    if (first_cta && fq.qcodes_out) {
+        constexpr int kEsz8 = (KIND == kF16 || KIND == kBF16) ? 16 : (KIND == kI8 ? 8 : 1);     // bits per element
+        const int bytes = dim_padded * kEsz8 / 8;
+        for (int i = tid; i < bytes / 16; i += NT)
+            reinterpret_cast<uint4*>(fq.qcodes_out)[i] = reinterpret_cast<const uint4*>(qenc)[i];
+    }
+}
+
 // NCH: 128-byte chunk groups per row (row_bytes = 128*NCH).  QREG: query in registers.
 template <int KIND, int NCH, int NW, int ITERS, int LPL, bool QREG>
 __global__ void __launch_bounds__((NW + 1) * 32, 1)
 scan_kernel(const uint8_t* __restrict__ codes, int64_t n_rows, const uint8_t* __restrict__ qcodes,
             uint32_t ord_min, int32_t b1_dim, uint64_t* __restrict__ cand, int stages,
-            const uint32_t* __restrict__ allow) {
+            const uint32_t* __restrict__ allow, FusedQuery fq) {
     constexpr bool kFloat = (KIND == kF16 || KIND == kBF16);
     constexpr int ROWB = NCH * 128;
     constexpr int ROWS_PER_WARP = 4 * ITERS;
@@ -93,6 +149,12 @@ scan_kernel(const uint8_t* __restrict__ codes, int64_t n_rows, const uint8_t* __
     }
 
     // ---------------------------------------------------------------- consumers
+    if (fq.src != nullptr) {                  // fused query encode: behind the ring, while the producer fills it
+        uint8_t* qenc = smem + (size_t)stages * TILE_BYTES;
+        encode_query_cta<KIND, NW * 32>(fq, kFloat ? NCH * 64 : (KIND == kI8 ? NCH * 128 : NCH * 1024),
+                                        reinterpret_cast<float*>(qenc + ROWB), qenc, threadIdx.x, blockIdx.x == 0);
+        qcodes = qenc;
+    }
     const int sub = lane & 7, grp = lane >> 3;
     float qf[(kFloat && QREG) ? QN : 1];
     uint32_t qi[kFloat ? 1 : QN];
@@ -230,7 +292,7 @@ template <int KIND, int NCH, int NW, int LPL>
 __global__ void __launch_bounds__((NW + 1) * 32, 1)
 scan_rows_kernel(const uint8_t* __restrict__ codes, int64_t n_rows, const uint8_t* __restrict__ qcodes,
                  uint32_t ord_min, int32_t b1_dim, uint64_t* __restrict__ cand, int stages,
-                 const uint32_t* __restrict__ allow) {
+                 const uint32_t* __restrict__ allow, FusedQuery fq) {
     static_assert(KIND == kI8 || KIND == kB1, "integer stores only");
     static_assert(NCH == 1 || NCH == 2, "rows of 128 or 256 bytes");
     constexpr int ROWB = NCH * 128;
@@ -269,6 +331,12 @@ scan_rows_kernel(const uint8_t* __restrict__ codes, int64_t n_rows, const uint8_
         return;
     }
 
+    if (fq.src != nullptr) {                  // fused query encode: behind the ring, while the producer fills it
+        uint8_t* qenc = smem + (size_t)stages * TILE_BYTES;
+        encode_query_cta<KIND, NW * 32>(fq, KIND == kI8 ? NCH * 128 : NCH * 1024,
+                                        reinterpret_cast<float*>(qenc + ROWB), qenc, threadIdx.x, blockIdx.x == 0);
+        qcodes = qenc;
+    }
     uint32_t qi[CH * 4];
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
@@ -575,21 +643,26 @@ cudaError_t launch_scan_int_multi(cudaStream_t st, crs_dtype store, const void* 
     return cudaErrorInvalidValue;
 }
 
+// dynamic shared memory of a scan: the ring, and behind it (fused query encode) the encoded query + its fp32 source
+static size_t scan_smem_bytes(int stages, int tile_bytes, size_t merge_bytes, int row_bytes, const FusedQuery& fq) {
+    size_t smem = (size_t)stages * tile_bytes;
+    if (fq.src != nullptr) smem += (size_t)row_bytes + (size_t)fq.dim * sizeof(float) + 16;
+    return smem < merge_bytes ? merge_bytes : smem;
+}
+
 template <int KIND, int NCH, int NW, int LPL>
 static cudaError_t launch_rows(cudaStream_t st, const void* codes, int64_t n, const void* qcodes, uint32_t ord_min,
-                               int32_t b1_dim, uint64_t* cand, int grid, const uint32_t* allow) {
+                               int32_t b1_dim, uint64_t* cand, int grid, const uint32_t* allow, const FusedQuery& fq) {
     constexpr int TILE_BYTES = NW * 32 * NCH * 128;
     constexpr int M = 32 * LPL;
     int stages = (200 * 1024) / TILE_BYTES;
     if (stages > kScanMaxStages) stages = kScanMaxStages;
-    size_t smem = (size_t)stages * TILE_BYTES;
-    const size_t merge_bytes = (size_t)NW * M * sizeof(uint64_t);
-    if (smem < merge_bytes) smem = merge_bytes;
+    const size_t smem = scan_smem_bytes(stages, TILE_BYTES, (size_t)NW * M * sizeof(uint64_t), NCH * 128, fq);
     auto kern = scan_rows_kernel<KIND, NCH, NW, LPL>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, (NW + 1) * 32, smem, st>>>(reinterpret_cast<const uint8_t*>(codes), n,
-                                            reinterpret_cast<const uint8_t*>(qcodes), ord_min, b1_dim, cand, stages, allow);
+                                            reinterpret_cast<const uint8_t*>(qcodes), ord_min, b1_dim, cand, stages, allow, fq);
     return cudaGetLastError();
 }
 
@@ -597,35 +670,33 @@ template <int KIND, int NCH>
 static cudaError_t rows_by_lpl(cudaStream_t st, const void* codes, int64_t n, const void* qcodes, uint32_t ord_min,
                                int32_t b1_dim, uint64_t* cand, const ScanPlan& p) {
     constexpr int NW = (NCH == 1) ? 16 : 8;          // 64 query registers per lane at NCH = 2
-    if (p.lpl == 1) return launch_rows<KIND, NCH, NW, 1>(st, codes, n, qcodes, ord_min, b1_dim, cand, p.grid, p.allow);
-    if (p.lpl == 4) return launch_rows<KIND, NCH, NW, 4>(st, codes, n, qcodes, ord_min, b1_dim, cand, p.grid, p.allow);
+    if (p.lpl == 1) return launch_rows<KIND, NCH, NW, 1>(st, codes, n, qcodes, ord_min, b1_dim, cand, p.grid, p.allow, p.fq);
+    if (p.lpl == 4) return launch_rows<KIND, NCH, NW, 4>(st, codes, n, qcodes, ord_min, b1_dim, cand, p.grid, p.allow, p.fq);
     return cudaErrorInvalidValue;
 }
 
 template <int KIND, int NCH, int NW, int ITERS, int LPL, bool QREG>
 static cudaError_t launch_one(cudaStream_t st, const void* codes, int64_t n, const void* qcodes, uint32_t ord_min,
-                              int32_t b1_dim, uint64_t* cand, int grid, const uint32_t* allow) {
+                              int32_t b1_dim, uint64_t* cand, int grid, const uint32_t* allow, const FusedQuery& fq) {
     constexpr int TILE_BYTES = NW * 4 * ITERS * NCH * 128;
     constexpr int M = 32 * LPL;
     int stages = (200 * 1024) / TILE_BYTES;
     if (stages > kScanMaxStages) stages = kScanMaxStages;
     if (stages < 2) return cudaErrorInvalidConfiguration;
-    size_t smem = (size_t)stages * TILE_BYTES;
-    const size_t merge_bytes = (size_t)NW * M * sizeof(uint64_t);
-    if (smem < merge_bytes) smem = merge_bytes;
+    const size_t smem = scan_smem_bytes(stages, TILE_BYTES, (size_t)NW * M * sizeof(uint64_t), NCH * 128, fq);
     auto kern = scan_kernel<KIND, NCH, NW, ITERS, LPL, QREG>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, (NW + 1) * 32, smem, st>>>(reinterpret_cast<const uint8_t*>(codes), n,
-                                            reinterpret_cast<const uint8_t*>(qcodes), ord_min, b1_dim, cand, stages, allow);
+                                            reinterpret_cast<const uint8_t*>(qcodes), ord_min, b1_dim, cand, stages, allow, fq);
     return cudaGetLastError();
 }
 
 template <int KIND, int NCH, int NW, int ITERS, bool QREG>
 static cudaError_t by_lpl(cudaStream_t st, const void* codes, int64_t n, const void* qcodes, uint32_t ord_min,
                           int32_t b1_dim, uint64_t* cand, const ScanPlan& p) {
-    if (p.lpl == 1) return launch_one<KIND, NCH, NW, ITERS, 1, QREG>(st, codes, n, qcodes, ord_min, b1_dim, cand, p.grid, p.allow);
-    if (p.lpl == 4) return launch_one<KIND, NCH, NW, ITERS, 4, QREG>(st, codes, n, qcodes, ord_min, b1_dim, cand, p.grid, p.allow);
+    if (p.lpl == 1) return launch_one<KIND, NCH, NW, ITERS, 1, QREG>(st, codes, n, qcodes, ord_min, b1_dim, cand, p.grid, p.allow, p.fq);
+    if (p.lpl == 4) return launch_one<KIND, NCH, NW, ITERS, 4, QREG>(st, codes, n, qcodes, ord_min, b1_dim, cand, p.grid, p.allow, p.fq);
     return cudaErrorInvalidValue;
 }
 

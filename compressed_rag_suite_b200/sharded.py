@@ -71,6 +71,7 @@ class PeerExchange:
         self._h = C.c_void_p()
         N.check(self._lib.crs_exchange_create(C.byref(self._h), int(device), int(rank), int(world), int(max_nq), int(max_k)))
         self.device, self.rank, self.world, self.max_nq, self.max_k = int(device), int(rank), int(world), int(max_nq), int(max_k)
+        self.has_shards = False
 
     def close(self) -> None:
         if self._h:
@@ -128,6 +129,77 @@ class PeerExchange:
         N.check(self._lib.crs_exchange_merge(self._h, C.c_void_p(st), int(nq), int(k), int(is_int), C.c_void_p(ids.data_ptr()),
                                              C.c_void_p(sc.data_ptr()), C.c_void_p(cnt.data_ptr())))
         return ids, sc, cnt
+
+    # ---- the shards' stored rows, peer-mapped: candidate vectors without a second collective
+    def register_shards_distributed(self, index, group=None) -> None:
+        """Collective: every rank publishes the CUDA IPC handle, id base and row count of its shard of `index`
+        and maps the others'.  Call after the corpus is built (growing an index re-allocates its rows)."""
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import _native as N
+        h = (C.c_uint8 * 64)()
+        base, cnt = C.c_uint32(), C.c_int64()
+        n_local = len(index)
+        N.check(self._lib.crs_index_codes_handle(index._h, h if n_local else None, None, C.byref(base), C.byref(cnt)))
+        dev = torch.device("cuda", self.device)
+        mine = torch.zeros(64 + 16, dtype=torch.uint8, device=dev)
+        mine[:64] = torch.frombuffer(bytearray(bytes(h)), dtype=torch.uint8).to(dev)
+        meta = torch.tensor([base.value, cnt.value], dtype=torch.int64).view(torch.uint8).to(dev)
+        mine[64:] = meta
+        allm = torch.empty((self.world, 80), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allm, mine, group=group)
+        allm = allm.cpu()
+        handles = bytes(allm[:, :64].contiguous().numpy().tobytes())
+        metas = allm[:, 64:].contiguous().view(torch.int64).numpy()
+        bases = (C.c_uint32 * self.world)(*[int(v) for v in metas[:, 0]])
+        counts = (C.c_int64 * self.world)(*[int(v) for v in metas[:, 1]])
+        N.check(self._lib.crs_exchange_open_shards(self._h, index._h, C.c_char_p(handles), bases, counts))
+        dist.barrier(group=group)
+        self.has_shards = True
+
+    @staticmethod
+    def register_shards_local(exchanges, indexes) -> None:
+        """Single process: exchanges[r] / indexes[r] belong to rank r."""
+        import ctypes as C
+        from . import _native as N
+        world = len(exchanges)
+        ptrs, bases, counts = (C.c_void_p * world)(), (C.c_uint32 * world)(), (C.c_int64 * world)()
+        for r, ix in enumerate(indexes):
+            p, b, c = C.c_void_p(), C.c_uint32(), C.c_int64()
+            N.check(ix._lib.crs_index_codes_handle(ix._h, None, C.byref(p), C.byref(b), C.byref(c)))
+            ptrs[r], bases[r], counts[r] = p.value or 0, b.value, c.value
+        for r, e in enumerate(exchanges):
+            N.check(e._lib.crs_exchange_set_shards(e._h, indexes[r]._h, ptrs, bases, counts))
+            e.has_shards = True
+
+    def fetch_rows(self, ids, row_bytes: int):
+        """ids: int32 CUDA tensor (uint32 bit patterns, any shape) -> uint8 CUDA tensor ids.shape + (row_bytes,):
+        every candidate's stored row read from the GPU that owns it (pad ids -> zero rows)."""
+        import ctypes as C
+        import torch
+        from . import _native as N
+        ids = ids.contiguous()
+        out = torch.empty(tuple(ids.shape) + (int(row_bytes),), dtype=torch.uint8, device=ids.device)
+        st = torch.cuda.current_stream(ids.device).cuda_stream
+        N.check(self._lib.crs_exchange_fetch_rows(self._h, C.c_void_p(st), C.c_void_p(ids.data_ptr()), ids.numel(),
+                                                  C.c_void_p(out.data_ptr())))
+        return out
+
+    def score_rows(self, index, queries, ids):
+        """K8 on global ids wherever the rows live (crs_exchange_score_rows): -> [nq, m] canonical scores of
+        `index`'s store dtype; pad ids get the absent score."""
+        import ctypes as C
+        import torch
+        from . import _native as N
+        q, i = queries.contiguous(), ids.contiguous()
+        nq, m = i.shape
+        out = torch.empty((nq, m), dtype=torch.int32 if index.is_int else torch.float32, device=q.device)
+        index._use_torch_stream()
+        N.check(self._lib.crs_exchange_score_rows(index._h, self._h, C.c_void_p(q.data_ptr()), nq, C.c_void_p(i.data_ptr()), m,
+                                                  C.c_void_p(out.data_ptr())))
+        absent = torch.iinfo(torch.int32).min if index.is_int else -math.inf
+        return torch.where(i != -1, out, torch.full_like(out, absent))
 
     @classmethod
     def from_process_group(cls, device: int, max_nq: int, max_k: int, group=None) -> "PeerExchange":
@@ -277,14 +349,25 @@ def similarity_of(index, raw):
 class ShardedMMRSearcher(ShardedSearcher):
     """BASELINE config 4: global top-`fetch_k` over the row shards, then the reference's greedy MMR
     (rag/retrieval.py:219-277) over the STORED vectors of those candidates, first `k` of the
-    greedy order.  Candidate vectors are gathered by their owners and assembled with one MAX
-    all-reduce of [nq, fetch_k, row_bytes] bytes (38 KB per query at 100 x 384 int8)."""
+    greedy order.  With the peer exchange every rank reads the candidates' rows straight out of the
+    owning GPU's HBM (NVLink peer loads, no second collective); with exchange="nccl" the owners gather
+    their rows and one MAX all-reduce of [nq, fetch_k, row_bytes] bytes assembles them."""
+
+    def _shard_exchange(self, nq: int, k: int):
+        ex = self._peer_exchange(nq, k)
+        if not ex.has_shards:
+            ex.register_shards_distributed(self.index, self.group)
+        return ex
 
     def search_mmr(self, queries, k: int, fetch_k: int, diversity_penalty: float,
                    min_similarity: float = -math.inf):
         """-> (ids int32 [nq,k] (pad -1), similarity f32 [nq,k], relevance f64 [nq,k], counts [nq])."""
         import torch
         ids, raw, cnt = self.search(queries, fetch_k, min_similarity)
+        if self.world > 1 and self.exchange == "peer":
+            nq = queries.shape[0] if queries.dim() > 1 else 1
+            vecs = self._shard_exchange(nq, fetch_k).fetch_rows(ids, self.index.row_bytes)
+            return self.index.mmr_select(vecs, ids, raw, cnt, 1.0 - diversity_penalty, k)
         vecs = self.index.fetch_rows_device(ids)
         if self.world > 1:
             vecs = assemble_over_shards(vecs, self.group)
@@ -299,7 +382,7 @@ class TwoStageSearcher:
     Both indexes are row-sharded identically; per search: one allgather of the coarse
     candidates + one MAX all-reduce of [nq, fetch_k] fine scores."""
 
-    def __init__(self, coarse, fine, group=None, local_only: bool = False, row_source=None):
+    def __init__(self, coarse, fine, group=None, local_only: bool = False, row_source=None, exchange: str = "peer"):
         """row_source: optional callable ids (int32 CUDA [nq, m], uint32 bit patterns, pad -1) ->
         float32 CUDA [nq, m, dim], the candidates' ORIGINAL vectors, for corpora whose fine rows
         are not resident in HBM (1 B x 1024-d fp16 = 2 TB: re-materialised from the generator, or
@@ -307,10 +390,11 @@ class TwoStageSearcher:
         Every rank must be able to produce every candidate (no second collective)."""
         if row_source is None and (len(coarse) != len(fine) or coarse.row_base != fine.row_base):
             raise ValueError("coarse and fine index must hold the same rows")
-        self.coarse = ShardedSearcher(coarse, group, local_only)
+        self.coarse = ShardedSearcher(coarse, group, local_only, exchange=exchange)
         self.fine = fine
         self.group = group
         self.row_source = row_source
+        self._fine_ex = None                     # peer access to the fine shards (exchange="peer")
 
     def search(self, queries, k: int, fetch_k: int, min_similarity: float = -math.inf):
         """-> (ids int32 [nq,k] (uint32 bit patterns, pad -1), fine scores f32 [nq,k], counts [nq])."""
@@ -320,6 +404,13 @@ class TwoStageSearcher:
         if self.row_source is not None:
             fine = self.fine.score_vectors(queries, self.row_source(ids))
             fine = torch.where(ids != -1, fine, torch.full_like(fine, -math.inf))
+        elif self.coarse.world > 1 and self.coarse.exchange == "peer":
+            # the candidates' fine rows are read from the GPUs that own them (NVLink peer loads) and scored here:
+            # no second collective
+            if self._fine_ex is None:
+                self._fine_ex = PeerExchange.from_process_group(self.fine.device, 1, 1, self.group)
+                self._fine_ex.register_shards_distributed(self.fine, self.group)
+            fine = self._fine_ex.score_rows(self.fine, queries, ids)
         else:
             fine = self.fine.score_rows(queries, ids)
             if self.coarse.world > 1:

@@ -227,6 +227,24 @@ int crs_index_search_push(crs_index* idx, crs_exchange* ex, const void* queries,
 int crs_exchange_merge(crs_exchange* ex, void* cuda_stream, int nq, int k, int is_int,
                        uint32_t* out_ids, void* out_scores, int32_t* out_counts);
 
+/* Candidate vectors without a second collective (BASELINE configs 4 and 5: MMR over the top-100, fp16 rescoring of
+ * Hamming candidates): every rank maps the other ranks' stored rows (CUDA IPC handle of the code buffer, or the
+ * pointer itself inside one process) and reads the candidates' rows straight out of the owning GPU's HBM over
+ * NVLink.  Register the shards after the corpus is built (growing an index re-allocates its rows).
+ *   crs_index_codes_handle : IPC handle (64 bytes, may be NULL) / device pointer / id range of this index's rows
+ *   crs_exchange_open_shards / _set_shards : rank-ordered tables; `own` is this rank's index
+ *   crs_exchange_fetch_rows  : ids [n] (device) -> stored codes [n, row_bytes] (device); pad ids -> zero rows
+ *   crs_exchange_score_rows  : K8 on global ids wherever the rows live: queries [nq, dim] fp32, ids [nq, m]
+ *                              (device) -> canonical scores [nq, m] of idx's store dtype (pad ids: caller masks) */
+int crs_index_codes_handle(crs_index* idx, void* out_handle64, void** out_ptr, uint32_t* row_base, int64_t* count);
+int crs_exchange_open_shards(crs_exchange* ex, crs_index* own, const void* handles /* world x 64 bytes */,
+                             const uint32_t* row_bases, const int64_t* counts);
+int crs_exchange_set_shards(crs_exchange* ex, crs_index* own, void* const* codes_ptrs, const uint32_t* row_bases,
+                            const int64_t* counts);
+int crs_exchange_fetch_rows(crs_exchange* ex, void* cuda_stream, const uint32_t* ids, int n, void* out_codes);
+int crs_exchange_score_rows(crs_index* idx, crs_exchange* ex, const void* queries, int nq, const uint32_t* ids, int m,
+                            void* out_scores);
+
 /* replaces chromadb.PersistentClient(path) persistence + get_collection reload —
  * rag/indexing.py:32-34,46-55.  Raw code blob + small header; the host keeps
  * ids/documents/metadatas in a sidecar. */

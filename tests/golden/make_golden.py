@@ -22,6 +22,13 @@ Fixtures
                               expectation for the CUDA MMR kernel (incl. the numpy-2 scalar
                               typing paths).
   transform_golden.json       ``_distance_to_similarity`` and ``_rerank`` outputs.
+  pipeline_c1_golden.json     BASELINE config 1 shape: the reference's own ``RAGPipeline`` (rag/pipeline.py:85-163)
+                              — DocumentProcessor.process_string, TextChunker (semantic, code defaults 512/50),
+                              EmbeddingModel, VectorStore, ContextRetriever with config.json's retrieval keys
+                              (top_k 3, threshold 0.3, rerank, MMR 0.1) — over 14 synthetic "pages" and 20 queries,
+                              with stand-ins only for what cannot exist offline (tests/c1_standins.py: a hash-seeded
+                              SentenceTransformer, a regex punkt tokenizer).  Holds the chunks the reference's
+                              chunker produced and what ``RAGPipeline.retrieve`` returned.
 """
 import json
 import os
@@ -215,7 +222,70 @@ def transform_cases():
     print("transform_golden: ok")
 
 
+def pipeline_c1_cases():
+    """BASELINE configs[0] through the reference's RAGPipeline (see the module docstring)."""
+    import types
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import c1_standins as st
+    ri, rr, rc, fc = load_reference()
+    fc.PRECISION = "f16"
+    import rag.embedding as ref_embedding
+    import rag.chunking as ref_chunking
+    import rag.pipeline as ref_pipeline
+    stored_of = {}
+
+    class PipelineEmbedder(st.HashSentenceTransformer):
+        """Indexing and queries get the hash vectors; the MMR step's "re-embedding" of chunk texts gets the rows the
+        store holds for them (canonical fp16 codes as fp32), exactly like the retrieval golden does."""
+
+        def encode(self, texts, **kw):
+            out = super().encode(texts, **kw)
+            for i, t in enumerate([texts] if isinstance(texts, str) else list(texts)):
+                if t in stored_of:
+                    out[i] = stored_of[t]
+            return out
+
+    ref_embedding.SentenceTransformer = PipelineEmbedder
+    ref_chunking.nltk = types.SimpleNamespace(data=types.SimpleNamespace(load=lambda _p: st.RegexPunkt(), find=lambda _p: True),
+                                              download=lambda *a, **k: True)
+    cfg = {"chunking": {"strategy": "semantic"},                                   # code defaults 512 / 50 / 100 (SURVEY.md App. A.1)
+           "embedding": {"device": "cpu"},
+           "vector_store": {"collection_name": "c1_golden"},
+           "retrieval": {"top_k": 3, "similarity_threshold": 0.3, "rerank": True, "diversity_penalty": 0.1}}   # config.json:20-25
+    pipe = ref_pipeline.RAGPipeline(cfg)
+    pipe.setup(model_interface=types.SimpleNamespace(model_type="instruct"))     # the generator is never called
+    pages = st.make_pages()
+    # index once to learn the chunk texts, then register their stored rows for the MMR step
+    pipe.index_documents(pages, show_progress=False)
+    col = pipe.vector_store.collection
+    texts = list(col._docs)
+    x = np.stack(col._emb).astype(np.float32)
+    stored = encode.encode_rows(x, "f16", "cosine")[:, :x.shape[1]].astype(np.float32)
+    for t, v in zip(texts, stored):
+        stored_of[t] = v
+    queries = st.make_queries()
+    by_id = {cid: stored[i] for i, cid in enumerate(col._ids)}
+    orc = postprocess.OracleRetriever(pipe.vector_store, pipe.embedding_model, cfg["retrieval"],
+                                      lambda ids: np.stack([by_id[i] for i in ids]))
+    cases = []
+    for q in queries:
+        got = pipe.retrieve(q)
+        want = orc.retrieve(q)
+        if [g["chunk_id"] for g in got] != [w["chunk_id"] for w in want]:
+            print(f"  skip {q!r}: reference MMR sits on an fp32 summation-order tie")
+            continue
+        assert got == want, "oracle restatement differs from the reference pipeline"
+        cases.append({"query": q, "chunk_ids": [g["chunk_id"] for g in got], "scores": [g["score"] for g in got],
+                      "distances": [g["distance"] for g in got], "rerank_scores": [g.get("rerank_score") for g in got],
+                      "metadatas": [g["metadata"] for g in got], "context": pipe.retriever.get_context_string(q)})
+    with open(os.path.join(HERE, "pipeline_c1_golden.json"), "w") as f:
+        json.dump({"config": cfg, "n_pages": len(pages), "chunk_ids": list(col._ids), "chunk_texts": texts,
+                   "chunk_metas": list(col._metas), "cases": cases}, f, indent=0)
+    print(f"pipeline_c1_golden: {len(col._ids)} chunks from {len(pages)} pages, {len(cases)} of {len(queries)} queries kept")
+
+
 if __name__ == "__main__":
+    pipeline_c1_cases()
     retrieval_cases()
     mmr_dyadic_cases()
     transform_cases()

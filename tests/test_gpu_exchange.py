@@ -76,3 +76,38 @@ def test_world_one_exchange_is_the_plain_search():
     got = empty.search_sharded(ex, q, 10)                    # an empty shard still takes part in the step
     assert got[2].max() == 0 and np.all(got[0] == 0xFFFFFFFF)
     assert ex.status() == (False, 3)
+
+
+@pytest.mark.parametrize("store", ["f16", "i8"])
+def test_peer_shards_fetch_and_score_rows_equal_the_single_index(store):
+    """Candidate rows by global id out of the owning shard (peer-mapped code buffers; here: three shards side by
+    side on one device): the same bytes / canonical scores as the single index gives."""
+    import torch
+    n, dim, world = 9001, 384, 3
+    x, centres = clustered(n, dim, seed=420)
+    whole = ShardIndex(dim, dtype=store)
+    whole.add(x)
+    shards, exs = [], []
+    for r in range(world):
+        lo, hi = shard_bounds(n, world, r)
+        sh = ShardIndex(dim, dtype=store, row_base=lo)
+        sh.add(x[lo:hi])
+        shards.append(sh)
+        exs.append(PeerExchange(0, r, world, max_nq=8, max_k=8))
+    PeerExchange.wire_local(exs)
+    PeerExchange.register_shards_local(exs, shards)
+    q = queries_for(centres, x, 6, seed=421)
+    ids, raw, cnt = whole.search(q, 50)
+    ids_t = torch.from_numpy(ids.view(np.int32)).cuda()
+    ids_t[0, 3] = -1                                          # a pad id
+    want_rows = whole.fetch_rows(ids.reshape(-1)).reshape(6, 50, -1)
+    want_rows[0, 3] = 0
+    for r in range(world):
+        got = exs[r].fetch_rows(ids_t, whole.row_bytes)
+        torch.cuda.synchronize()
+        assert np.array_equal(got.cpu().numpy(), want_rows)
+        sc = exs[r].score_rows(shards[r], torch.from_numpy(q).cuda(), ids_t)
+        torch.cuda.synchronize()
+        sc = sc.cpu().numpy()
+        assert np.array_equal(sc[0, 4:].view(np.uint32), raw[0, 4:].view(np.uint32)) and np.array_equal(sc[1:].view(np.uint32), raw[1:].view(np.uint32))
+        assert sc[0, 3] == (np.iinfo(np.int32).min if whole.is_int else -np.inf)

@@ -379,3 +379,37 @@ def test_persistence_is_append_only_and_survives_torn_writes(tmp_path):
     os.makedirs(str(tmp_path / "chroma"), exist_ok=True)
     open(str(tmp_path / "chroma" / "chroma.sqlite3"), "wb").close()
     assert VectorStore({"collection_name": "col", "persist_directory": str(tmp_path / "chroma")}).collection is None
+
+
+def test_config1_pipeline_equals_the_reference_ragpipeline(golden_dir):
+    """BASELINE configs[0] shape: 14 page-sized chunks, top_k 3, threshold 0.3, rerank, MMR 0.1.  The expected outputs
+    come from the reference's OWN RAGPipeline (tests/golden/make_golden.py: pipeline_c1_cases) with the same stand-in
+    embedder; here its VectorStore / ContextRetriever are replaced by this repo's."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import c1_standins as st
+    g = json.load(open(os.path.join(golden_dir, "pipeline_c1_golden.json")))
+    chunks = [Chunk(text=t, chunk_id=cid, start_char=0, end_char=len(t), **m)
+              for t, cid, m in zip(g["chunk_texts"], g["chunk_ids"], g["chunk_metas"])]
+
+    class Embedder:                                     # EmbeddingModel stand-in: rag/embedding.py:47-73
+        model = st.HashSentenceTransformer()
+
+        def embed(self, texts, show_progress=False):
+            return self.model.encode([texts] if isinstance(texts, str) else texts)
+
+    emb = Embedder()
+    vs = VectorStore(g["config"]["vector_store"])
+    vs.create_index(chunks, emb.embed([c.text for c in chunks]))
+    r = ContextRetriever(vs, emb, g["config"]["retrieval"])
+    assert len(g["cases"]) >= 15
+    for case in g["cases"]:
+        got = r.retrieve(case["query"])
+        assert [c["chunk_id"] for c in got] == case["chunk_ids"], case["query"]
+        assert [c["score"] for c in got] == case["scores"]
+        assert [c["distance"] for c in got] == case["distances"]
+        assert [c.get("rerank_score") for c in got] == case["rerank_scores"]
+        assert [c["metadata"] for c in got] == case["metadatas"]
+        assert r.get_context_string(case["query"]) == case["context"]
+    batch = r.retrieve_batch([c["query"] for c in g["cases"]])
+    assert [[c["chunk_id"] for c in one] for one in batch] == [c["chunk_ids"] for c in g["cases"]]

@@ -69,11 +69,12 @@ def main():
         timed_out, step = peer._peer.status()
         report(f"exchange of {store}: no wait timed out (step {step})", not timed_out)
         if store in ("f16", "i8"):
-            m = ShardedMMRSearcher(shard)
             w = ShardedMMRSearcher(full, local_only=True)
-            got = m.search_mmr(q[:8], 10, 100, 0.1)
             want = w.search_mmr(q[:8], 10, 100, 0.1)
-            report(f"top-100 -> MMR -> 10 {store}", same(got, want))
+            got = ShardedMMRSearcher(shard, exchange="peer", max_nq=512).search_mmr(q[:8], 10, 100, 0.1)
+            report(f"top-100 -> MMR -> 10 {store} [candidate rows by NVLink peer loads]", same(got, want))
+            got = ShardedMMRSearcher(shard, exchange="nccl").search_mmr(q[:8], 10, 100, 0.1)
+            report(f"top-100 -> MMR -> 10 {store} [candidate rows by MAX all-reduce]", same(got, want))
         full.close(); shard.close()
 
     dim, n = 1024, 50000
@@ -85,8 +86,10 @@ def main():
     sc, sf = ShardIndex(dim, dtype="b1", device=local, row_base=lo), ShardIndex(dim, dtype="f16", device=local, row_base=lo)
     sc.add(x[lo:hi]); sf.add(x[lo:hi])
     want = TwoStageSearcher(fc, ff, local_only=True).search(q, 10, 100)      # no collectives involved
-    got = TwoStageSearcher(sc, sf).search(q, 10, 100)
-    report("Hamming top-100 -> fp16 rescoring -> 10", same(got, want))
+    got = TwoStageSearcher(sc, sf, exchange="peer").search(q, 10, 100)
+    report("Hamming top-100 -> fp16 rescoring -> 10 [fine rows by NVLink peer loads]", same(got, want))
+    got = TwoStageSearcher(sc, sf, exchange="nccl").search(q, 10, 100)
+    report("Hamming top-100 -> fp16 rescoring -> 10 [fine scores by MAX all-reduce]", same(got, want))
 
     dist.barrier()
     dist.destroy_process_group()
