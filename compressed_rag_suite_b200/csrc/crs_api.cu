@@ -115,6 +115,8 @@ struct crs_index {
     int64_t sample_rows = 0;    // rows of an optional sample pass that seeds the contraction's per-query floors (0 = off)
     int share_floor = 1;        // contraction: the slices of a query share their k-th best score while the launch runs
     int gemm_warm = 8;          // contraction: first tiles of every slice that only seed the floor and are redone last
+    int gemm_lockstep = 6;      // contraction: tiles a cluster may run ahead of the slowest cluster streaming the same corpus
+                                // slice (they share the slice through L2 only while they stay close); 0 = off
     int fuse_encode = 1;        // single-query scans encode the query in their own prologue (no separate encode launch)
     int short_lists = 1;        // integer scans with k > 32 keep 32 keys per CTA + certification (0 = full 128-key lists)
     int multi_scan = 8;         // largest group of short-row integer queries that shares one corpus pass (<= 1: off)
@@ -324,6 +326,7 @@ int crs_index_set_option(crs_index* ix, const char* name, int64_t value) {
     else if (!strcmp(name, "sample_rows")) ix->sample_rows = value;
     else if (!strcmp(name, "share_floor")) ix->share_floor = (int)value;
     else if (!strcmp(name, "fuse_encode")) ix->fuse_encode = (int)value;
+    else if (!strcmp(name, "gemm_lockstep")) ix->gemm_lockstep = (int)value;
     else if (!strcmp(name, "gemm_warm")) ix->gemm_warm = (int)std::max<int64_t>(0, std::min<int64_t>(value, 64));
     else if (!strcmp(name, "eps_scale")) ix->eps_scale = (double)value / 1000.0;
     else if (!strcmp(name, "profiling")) {
@@ -649,11 +652,16 @@ static int search_impl(crs_index* ix, const void* queries, int nq, int k, float 
                 if (sampling || sharing) {
                     const int slices_full = crs::gemm_n_slices(ix->count, nq, ix->num_sms, ix->gemm_cluster);
                     const size_t nq_pad = ((size_t)nq + 127) / 128 * 128;
-                    const size_t words = nq_pad + (sharing ? nq_pad * (size_t)slices_full * L : 0);
+                    const size_t pub_words = sharing ? nq_pad * (size_t)slices_full * L : 0;
+                    const size_t prog_words = ix->gemm_lockstep
+                        ? (size_t)crs::gemm_progress_words(ix->count, nq, ix->num_sms, ix->gemm_cluster) : 0;
+                    const size_t words = nq_pad + pub_words + prog_words;
                     CRS_CUDA(ix->floors.ensure(words));
                     CRS_CUDA(cudaMemsetAsync(ix->floors.p, 0, words * sizeof(uint32_t), st));
                     fl.tau_q = ix->floors.p;
                     fl.pub = sharing ? ix->floors.p + nq_pad : nullptr;
+                    fl.progress = prog_words ? ix->floors.p + nq_pad + pub_words : nullptr;
+                    fl.lead_tiles = ix->gemm_lockstep;
                     fl.qnorms = ix->qnorms.p;
                     fl.margin_rel = is_float ? 3.0f * fa.eps_rel * ix->row_norm_bound : 0.f;
                     if (is_float) fa.tau_q = fl.tau_q;

@@ -112,6 +112,7 @@ cudaError_t launch_score_rows(cudaStream_t st, const void* codes, int64_t n_rows
 bool gemm_supported(int row_bytes, int k);
 int gemm_list_len(int k);
 int gemm_n_slices(int64_t n, int nq, int num_sms, int cluster);     // lists per query the launch will write
+int gemm_progress_words(int64_t n, int nq, int num_sms, int cluster);   // words of GemmFloorArgs::progress (zeroed by the caller)
 // Per-query floors of the contraction.  tau_q: [nq] ORDERABLE 32-bit scores (orderable_f32 / orderable_i32,
 // 0 = none), read when a slice starts and — when `pub` is given — raised while the launch runs: the slices
 // of a query publish their lists' scores into pub ([nq][n_slices][gemm_list_len(k)] uint32, zeroed by the
@@ -122,6 +123,9 @@ struct GemmFloorArgs {
     uint32_t* pub;
     const float* qnorms;
     float margin_rel;
+    uint32_t* progress = nullptr;   // optional [gemm_progress_words] zeroed words: the clusters of a corpus slice stay in
+                                    // lock-step (within a few MB), so that they share the slice through L2
+    int lead_tiles = 6;             // tiles (256 rows) a cluster may run ahead of the slowest cluster of its slice
 };
 cudaError_t launch_gemm_topk(cudaStream_t st, const void* codes, int64_t n, int row_bytes, int kind,
                              const void* qcodes, int nq, int k, uint32_t tau_pre_bits, uint64_t* cand, int num_sms,

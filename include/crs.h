@@ -116,6 +116,9 @@ int crs_index_last_stats(const crs_index* idx, crs_search_stats* out);
  *   "gemm_prefetch" [0]  corpus tiles prefetched into L2 ahead of the TMA ring
  *   "share_floor"   [1]  contraction: the corpus slices of a query share their k-th best score while the launch runs
  *   "gemm_warm"     [8]  contraction: first tiles of every slice that only seed the floor and are computed again last
+ *   "gemm_lockstep" [6]  contraction: tiles a cluster may run ahead of the slowest cluster streaming the same corpus slice
+ *                        (they share the slice through L2 only while they stay close); 0 = off
+ *   "fuse_encode"   [1]  single-query scans encode the query in their own prologue instead of a separate launch
  *   "sample_rows"   [0]  rows of an optional sample pass that seeds the contraction's per-query floors (0 = off)
  *   "multi_scan"    [8]  largest group of short-row integer queries that shares one corpus pass (<= 1 = off)
  *   "short_lists"   [1]  integer scans with k > 32 keep 32 keys per CTA + certification (0 = full 128-key lists)
