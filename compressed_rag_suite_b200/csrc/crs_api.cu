@@ -906,6 +906,9 @@ int crs_mmr(crs_index* ix, const void* vecs, const double* relevance, int nq, in
     if (nq < 0 || m < 0 || k_out <= 0) return fail(CRS_EINVAL, "bad sizes");
     if (nq == 0 || m == 0) return CRS_OK;
     if (m > 128) return fail(CRS_EINVAL, "m > 128 candidates not supported");
+    if ((size_t)m * (ix->row_bytes + 16) > 200 * 1024)
+        return fail(CRS_EINVAL, "candidate set too large for the MMR kernel's shared memory (m * (row_bytes + 16) must stay below 200 KB: "
+                                "e.g. m <= 99 for 1024-d fp16 rows)");
     if (!vecs || !relevance || !out_order) return fail(CRS_EINVAL, "NULL buffer");
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
@@ -931,6 +934,8 @@ int crs_mmr_select(crs_index* ix, const void* vecs, const uint32_t* ids, const v
     if (nq < 0 || m <= 0 || k_out <= 0) return fail(CRS_EINVAL, "bad sizes");
     if (nq == 0) return CRS_OK;
     if (m > 128) return fail(CRS_EINVAL, "m > 128 candidates not supported");
+    if ((size_t)m * (ix->row_bytes + 16) > 200 * 1024)
+        return fail(CRS_EINVAL, "candidate set too large for the MMR kernel's shared memory (m * (row_bytes + 16) must stay below 200 KB)");
     const void* ptrs[] = {vecs, ids, raw_scores, counts, out_ids, out_sims, out_scores, out_counts};
     for (const void* p : ptrs)
         if (!is_device_ptr(p)) return fail(CRS_EINVAL, "crs_mmr_select takes device buffers");
