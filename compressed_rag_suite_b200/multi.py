@@ -154,11 +154,16 @@ class MultiDeviceIndex:
         # one copy of the queries per device (pinned host -> device, or a peer copy), all asynchronous
         if not is_t:
             host = torch.from_numpy(q0)
-        for r, sh in enumerate(self.shards):
+        # (all copies first: a device-to-device copy is ordered behind the work already enqueued on its source device,
+        # so copying after device 0's search has been enqueued would serialise the devices)
+        qds = []
+        for sh in self.shards:
             dev = torch.device("cuda", sh.device)
             with torch.cuda.device(dev):
-                qd = q0.to(dev, non_blocking=True) if is_t else host.to(dev, non_blocking=True)
-                sh.search_push(exs[r], qd, k, min_similarity, allow=allows[r])
+                qds.append(q0.to(dev, non_blocking=True) if is_t else host.to(dev, non_blocking=True))
+        for r, sh in enumerate(self.shards):
+            with torch.cuda.device(torch.device("cuda", sh.device)):
+                sh.search_push(exs[r], qds[r], k, min_similarity, allow=allows[r])
         with torch.cuda.device(torch.device("cuda", self.devices[0])):
             ids, sc, cnt = exs[0].merge(nq, k, self.is_int)
             if is_t:
