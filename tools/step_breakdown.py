@@ -11,6 +11,9 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
+import compressed_rag_suite_b200._native as _N
+if os.environ.get("CRS_LIB"):                      # A/B of two builds of the library on one box
+    _N.LIB_PATH = os.path.abspath(os.environ["CRS_LIB"])
 from compressed_rag_suite_b200.index import ShardIndex
 
 
