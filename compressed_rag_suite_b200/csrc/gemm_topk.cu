@@ -9,7 +9,7 @@
 // blockIdx = slice * n_qtiles + qtile, so the CTAs that stream the same corpus slice are
 // launched next to each other and share it through L2.
 //
-// Roles inside a CTA (192 threads, 1 CTA / SM):
+// Roles inside a CTA (9 warps = 288 threads, 1 CTA / SM):
 //   warp 0  TMA producer : loads the CTA's query tile once (A operand, stays resident in
 //           smem: KCH chunks of [128 x 64] fp16, SWIZZLE_128B), then streams corpus tiles
 //           as [256 rows x 64 k] chunks (B operand) through a STAGES-deep mbarrier ring.
@@ -20,7 +20,9 @@
 //   warps 2-5 epilogue   : TMEM lane = query, column = corpus row.  Each thread reads its
 //           query's 256 scores in 32-column slabs (tcgen05.ld.32x32b.x32), tests the slab
 //           maximum against its running threshold (the L-th best so far), and only on a
-//           hit walks the slab and inserts into a sorted register list of L keys.
+//           hit walks the slab and inserts into a sorted register list of L keys.  The first
+//           `warm_tiles` tiles of a slice are only looked at (group maxima seed the floor) and are
+//           computed a second time at the end of the slice (deferred warm-up, see n_warm).
 //   warps 6-7  floor sharing: the slices of a query tile run on different SMs and each keeps its own
 //           list, so without help every (query, slice) list warms up on its own (16 ln(n/16) inserts
 //           each, ~13x what one list over the whole shard would need).  Epilogue threads publish
@@ -29,7 +31,11 @@
 //           lists of the queries assigned to its CTA and stores the k-th best score of the union as
 //           the query's floor (tau_q), which every slice re-reads once per tile.  A floor is valid
 //           whenever k published scores reach it — k distinct rows score at least that — whatever
-//           mix of old and new slot values a racing reader sees.
+//           mix of old and new slot values a racing reader sees: the published slots are scores of
+//           distinct rows and only ever grow (atomicMax), so for any threshold t the number of slots
+//           a reader sees at or above t never exceeds the number of rows that really score >= t.
+//   warp 8  slice lock-step monitor: keeps the clusters that stream the same corpus slice within a few
+//           tiles of each other so that they share the slice through L2 (see lock_allowed).
 // At the end every thread writes its sorted list: cand[q][slice][0..L) (stride M = 32).
 // finalize.cu merges the slices' lists, rescores the candidates exactly in fp64,
 // certifies the top-k and falls back to the exhaustive fp64 pass when it cannot.
