@@ -130,6 +130,9 @@ struct crs_index {
     DevScratch<int32_t> flags, counts_dev;
     DevScratch<uint32_t> ids_dev;
     DevScratch<uint8_t> scores_dev;
+    DevScratch<uint8_t> out_pack;               // host-output searches: [ids | scores | counts], copied back in one piece
+    uint8_t* h_pack = nullptr;                  // pinned staging of that copy
+    size_t h_pack_cap = 0;
     DevScratch<uint32_t> allow_dev, floors;     // floors: [tau_q (nq, padded to 128) | pub lists] of the contraction
     int32_t* n_flagged = nullptr;      // device counters: [0] uncertified this search, [1] since create,
                                        // [2] float bits of the largest |fast - exact| score seen in finalize
@@ -285,7 +288,8 @@ int crs_index_destroy(crs_index* ix) {
         if (ix->ev_switch) cudaEventDestroy(ix->ev_switch);
         ix->qsrc.release(); ix->qnorms.release(); ix->norms_tmp.release(); ix->qcodes.release();
         ix->stage_rows.release(); ix->vec_codes.release(); ix->cand.release(); ix->flags.release(); ix->counts_dev.release();
-        ix->ids_dev.release(); ix->scores_dev.release(); ix->allow_dev.release(); ix->floors.release();
+        ix->ids_dev.release(); ix->scores_dev.release(); ix->allow_dev.release(); ix->floors.release(); ix->out_pack.release();
+        if (ix->h_pack) cudaFreeHost(ix->h_pack);
     }
     delete ix;
     return CRS_OK;
@@ -525,11 +529,18 @@ static int search_impl(crs_index* ix, const void* queries, int nq, int k, float 
     const size_t nk = (size_t)nq * k;
 
     uint32_t* d_ids = out_ids; void* d_scores = out_scores; int32_t* d_counts = out_counts;
-    if (!out_dev) {
-        CRS_CUDA(ix->ids_dev.ensure(nk));
-        CRS_CUDA(ix->scores_dev.ensure(nk * 4));
-        CRS_CUDA(ix->counts_dev.ensure((size_t)nq));
-        d_ids = ix->ids_dev.p; d_scores = ix->scores_dev.p; d_counts = ix->counts_dev.p;
+    const size_t pack_bytes = nk * 8 + (size_t)nq * 4;       // host results: [ids | scores | counts] in ONE device buffer,
+    if (!out_dev) {                                          // so that they come back in one copy instead of three
+        CRS_CUDA(ix->out_pack.ensure(pack_bytes));
+        if (ix->h_pack_cap < pack_bytes) {
+            if (ix->h_pack) cudaFreeHost(ix->h_pack);
+            ix->h_pack = nullptr; ix->h_pack_cap = 0;
+            CRS_CUDA(cudaHostAlloc(&ix->h_pack, pack_bytes + 4096, cudaHostAllocDefault));
+            ix->h_pack_cap = pack_bytes + 4096;
+        }
+        d_ids = reinterpret_cast<uint32_t*>(ix->out_pack.p);
+        d_scores = ix->out_pack.p + nk * 4;
+        d_counts = reinterpret_cast<int32_t*>(ix->out_pack.p + nk * 8);
     }
     // with an exchange the local search writes into the exchange's staging area and the exchange kernel
     // produces the final (global) result
@@ -540,11 +551,14 @@ static int search_impl(crs_index* ix, const void* queries, int nq, int k, float 
     }
 
     bool copied = false;
+    // device pack -> pinned staging (one copy, enqueued); unpack_out() moves it into the caller's arrays after the sync
     auto copy_out = [&]() -> cudaError_t {
-        cudaError_t e = cudaMemcpyAsync(out_ids, f_ids, nk * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(out_scores, f_scores, nk * 4, cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(out_counts, f_counts, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
-        return e;
+        return cudaMemcpyAsync(ix->h_pack, f_ids, pack_bytes, cudaMemcpyDeviceToHost, st);
+    };
+    auto unpack_out = [&]() {
+        memcpy(out_ids, ix->h_pack, nk * 4);
+        memcpy(out_scores, ix->h_pack + nk * 4, nk * 4);
+        memcpy(out_counts, ix->h_pack + nk * 8, (size_t)nq * 4);
     };
 
     if (ix->count == 0) {
@@ -723,6 +737,7 @@ static int search_impl(crs_index* ix, const void* queries, int nq, int k, float 
                     CRS_CUDA(cudaStreamSynchronize(st));
                     need_exact = nf > 0;
                     copied = !need_exact;
+                    if (copied) unpack_out();
                 }
             }
         } else {
@@ -762,6 +777,7 @@ static int search_impl(crs_index* ix, const void* queries, int nq, int k, float 
     if (!out_dev && !copied) {
         CRS_CUDA(copy_out());
         CRS_CUDA(cudaStreamSynchronize(st));
+        unpack_out();
     }
     ix->stats.kernel_launches = launches;
     ix->stats.searches_total += nq;

@@ -301,7 +301,18 @@ def main():
     q_host.copy_(q)
     q_stage = torch.empty_like(q)
 
+    q_np = q_host.numpy()
+    out_np = None
+    if cfg in ("c2", "c4t") and world == 1:
+        out_np = (torch.empty((a.batch, k), dtype=torch.int32).pin_memory().numpy(),
+                  torch.empty((a.batch, k), dtype=torch.int32 if ix.is_int else torch.float32).pin_memory().numpy(),
+                  torch.empty((a.batch,), dtype=torch.int32).pin_memory().numpy())
+
     def step_e2e():
+        if out_np is not None:
+            # straight through the C ABI with HOST buffers: crs_index_search copies the query in, searches (the scan
+            # encodes the query itself), brings ids / scores / counts back in one copy and returns
+            return ix.search(q_np, k, thr_cos, out=out_np)
         q_stage.copy_(q_host, non_blocking=True)
         if cfg in ("c2", "c4t"):
             out = searcher.search(q_stage, k, thr_cos)
