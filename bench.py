@@ -292,10 +292,10 @@ def run_ours(a):
             # runs the search, copies ids / scores / counts out and returns when they are on the host
             ix.search(q_host_np, a.k, out=out_np)
             return
-        if a.exchange == "peer":
+        if searcher.exchange == "peer" and searcher._peer is not None:
             # the same through crs_index_search_sharded: H2D of the queries, local search, peer-memory
             # exchange + merge, D2H of the global result, all inside the one C-ABI call
-            ix.search_sharded(searcher._peer_exchange(a.batch, a.k), q_host_np, a.k, out=out_np)
+            ix.search_sharded(searcher._peer, q_host_np, a.k, out=out_np)
             return
         q_stage.copy_(q_host, non_blocking=True)                 # H2D of this step's queries
         ids, sc, cnt = searcher.search(q_stage, a.k)
@@ -360,7 +360,7 @@ def run_ours(a):
 
     # ---- the same step replayed from ONE CUDA graph (extra figure: no launch gaps between the kernels)
     graph_ms = None
-    if world == 1 or a.exchange == "peer":
+    if world == 1 or searcher.exchange == "peer":
         try:
             gs = searcher.capture(a.batch, a.k)
             gs.queries.copy_(q_dev)
@@ -379,7 +379,7 @@ def run_ours(a):
     # ---- the other exchange, for comparison (N > 1)
     other = None
     if world > 1:
-        alt = ShardedSearcher(ix, exchange="nccl" if a.exchange == "peer" else "peer", max_nq=max(a.batch, 64), max_k=max(a.k, 16))
+        alt = ShardedSearcher(ix, exchange="nccl" if searcher.exchange == "peer" else "peer", max_nq=max(a.batch, 64), max_k=max(a.k, 16))
         alt_total, _ = timed(lambda: alt.search(q_dev, a.k), a.steps, 3)
         other = {"exchange": alt.exchange, "ms_per_step": alt_total / a.steps}
 
@@ -470,7 +470,7 @@ def run_ours(a):
                 "ms_per_step": e2e_total / a.steps, "kernel_ms": sum(e2e_kms) / len(e2e_kms),
                 "call": "crs_index_search with pinned host buffers" if world == 1 else
                         ("crs_index_search_sharded with pinned host buffers (H2D, local search, peer-memory exchange + merge, D2H)"
-                         if a.exchange == "peer" else
+                         if searcher.exchange == "peer" else
                          "pinned host -> device copy, sharded search (NCCL allgather + merge), device -> pinned host copy")},
         "gpu_launches": (stats["kernel_launches"] + searcher.merge_launches) * a.steps,
         "launches_per_step": stats["kernel_launches"] + searcher.merge_launches,
@@ -482,8 +482,9 @@ def run_ours(a):
         "clocks": sampler.summary(t_load0, t_load1),
     }
     if world > 1:
-        out["exchange"] = ("peer-memory exchange + merge kernel (NVLink P2P stores, CUDA IPC)" if a.exchange == "peer"
-                           else "NCCL all_gather_into_tensor + merge kernel")
+        out["exchange"] = ("peer-memory exchange + merge kernel (NVLink P2P stores, CUDA IPC)" if searcher.exchange == "peer"
+                           else "NCCL all_gather_into_tensor + merge kernel" +
+                                (" (peer memory unavailable on this box)" if a.exchange == "peer" else ""))
         out["other_exchange"] = other
         out["sharded_equals_single"] = sharded_equals_single
         out["exchange_steps"] = xstat

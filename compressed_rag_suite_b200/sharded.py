@@ -54,6 +54,10 @@ def exchange_candidates(packed, group=None):
     return out
 
 
+class PeerExchangeUnavailable(RuntimeError):
+    """Peer memory between the ranks' GPUs cannot be set up (raised on every rank together)."""
+
+
 class PeerExchange:
     """One rank's ``crs_exchange``: a receive buffer every peer GPU stores its local top-k into (NVLink
     peer memory), so that the exchange + merge of a sharded search is one kernel of libcrs instead of an
@@ -203,15 +207,44 @@ class PeerExchange:
 
     @classmethod
     def from_process_group(cls, device: int, max_nq: int, max_k: int, group=None) -> "PeerExchange":
-        """Collective: every rank of the group creates its exchange and maps every peer's receive buffer."""
+        """Collective: every rank of the group creates its exchange and maps every peer's receive buffer.
+        The ranks agree (MIN all-reduce of a success flag) after each local step, so a rank on which peer
+        memory cannot be set up — no P2P between the devices, CUDA IPC not permitted in this container —
+        makes EVERY rank raise ``PeerExchangeUnavailable`` together instead of leaving the others in a collective."""
         import torch
         import torch.distributed as dist
         rank, world = dist.get_rank(group), dist.get_world_size(group)
-        ex = cls(device, rank, world, max_nq, max_k)
-        mine = torch.frombuffer(bytearray(ex.ipc_handle()), dtype=torch.uint8).to(torch.device("cuda", device))
-        allh = torch.empty((world, 64), dtype=torch.uint8, device=mine.device)
-        dist.all_gather_into_tensor(allh, mine, group=group)
-        ex.open_peers(bytes(allh.cpu().numpy().tobytes()))
+        dev = torch.device("cuda", device)
+
+        def agree(ok: bool, what: str, err) -> None:
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()) == 0:
+                raise PeerExchangeUnavailable(f"{what} failed on at least one rank" + (f" (here: {err})" if err else ""))
+
+        import os
+        ex, err, handle = None, None, b"\0" * 64
+        try:
+            if os.environ.get("CRS_DISABLE_PEER_EXCHANGE"):      # knob (and test hook for the agreed fallback)
+                raise RuntimeError("disabled by CRS_DISABLE_PEER_EXCHANGE")
+            ex = cls(device, rank, world, max_nq, max_k)
+            handle = ex.ipc_handle()
+        except Exception as e:  # noqa: BLE001
+            err = e
+        try:
+            agree(err is None, "creating the receive buffer / its IPC handle", err)
+            mine = torch.frombuffer(bytearray(handle), dtype=torch.uint8).to(dev)
+            allh = torch.empty((world, 64), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(allh, mine, group=group)
+            try:
+                ex.open_peers(bytes(allh.cpu().numpy().tobytes()))
+            except Exception as e:  # noqa: BLE001
+                err = e
+            agree(err is None, "mapping the peers' receive buffers", err)
+        except PeerExchangeUnavailable:
+            if ex is not None:
+                ex.close()
+            raise
         dist.barrier(group=group)
         return ex
 
@@ -258,7 +291,14 @@ class ShardedSearcher:
             if self._peer is not None:
                 self._peer.close()
             cap_nq, cap_k = max(nq, self._peer_cap[0]), min(128, max(k, self._peer_cap[1]))
-            self._peer = PeerExchange.from_process_group(self.index.device, cap_nq, cap_k, self.group)
+            self._peer = None
+            try:
+                self._peer = PeerExchange.from_process_group(self.index.device, cap_nq, cap_k, self.group)
+            except PeerExchangeUnavailable as e:
+                # every rank lands here together: use the NCCL exchange from now on (same results, one more launch)
+                import logging
+                logging.getLogger(__name__).warning(f"peer-memory exchange unavailable ({e}); using the NCCL allgather + merge kernel")
+                self.exchange = "nccl"
         return self._peer
 
     def search(self, queries, k: int, min_similarity: float = -math.inf):
@@ -271,8 +311,10 @@ class ShardedSearcher:
             return self.index.search(queries, k, min_similarity)
         if self.exchange == "peer" and queries.is_cuda:
             nq = queries.shape[0] if queries.dim() > 1 else 1
-            self.merge_launches = 0                      # the exchange kernel is counted by the library
-            return self.index.search_sharded(self._peer_exchange(nq, k), queries, k, min_similarity)
+            ex = self._peer_exchange(nq, k)              # may switch self.exchange to "nccl" (on every rank together)
+            if ex is not None:
+                self.merge_launches = 0                  # the exchange kernel is counted by the library
+                return self.index.search_sharded(ex, queries, k, min_similarity)
         # the local result is written straight into the send buffer ([0] ids, [1] raw-score bits) and the
         # merge reads the gathered buffer in place: search -> allgather -> merge, no pack / unpack copies
         nq = queries.shape[0] if queries.dim() > 1 else 1
@@ -298,6 +340,8 @@ class ShardedSearcher:
         gen.manual_seed(7)
         q = torch.randn((nq, ix.dim), dtype=torch.float32, device=dev, generator=gen)
         ex = self._peer_exchange(nq, k) if self.world > 1 else None
+        if self.world > 1 and ex is None:
+            raise ValueError("capture needs the peer exchange")
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):                      # warm-up sizes every scratch buffer (and takes two steps on every rank)
@@ -355,7 +399,7 @@ class ShardedMMRSearcher(ShardedSearcher):
 
     def _shard_exchange(self, nq: int, k: int):
         ex = self._peer_exchange(nq, k)
-        if not ex.has_shards:
+        if ex is not None and not ex.has_shards:
             ex.register_shards_distributed(self.index, self.group)
         return ex
 
@@ -366,8 +410,10 @@ class ShardedMMRSearcher(ShardedSearcher):
         ids, raw, cnt = self.search(queries, fetch_k, min_similarity)
         if self.world > 1 and self.exchange == "peer":
             nq = queries.shape[0] if queries.dim() > 1 else 1
-            vecs = self._shard_exchange(nq, fetch_k).fetch_rows(ids, self.index.row_bytes)
-            return self.index.mmr_select(vecs, ids, raw, cnt, 1.0 - diversity_penalty, k)
+            ex = self._shard_exchange(nq, fetch_k)
+            if ex is not None:
+                vecs = ex.fetch_rows(ids, self.index.row_bytes)
+                return self.index.mmr_select(vecs, ids, raw, cnt, 1.0 - diversity_penalty, k)
         vecs = self.index.fetch_rows_device(ids)
         if self.world > 1:
             vecs = assemble_over_shards(vecs, self.group)
@@ -408,9 +454,15 @@ class TwoStageSearcher:
             # the candidates' fine rows are read from the GPUs that own them (NVLink peer loads) and scored here:
             # no second collective
             if self._fine_ex is None:
-                self._fine_ex = PeerExchange.from_process_group(self.fine.device, 1, 1, self.group)
-                self._fine_ex.register_shards_distributed(self.fine, self.group)
-            fine = self._fine_ex.score_rows(self.fine, queries, ids)
+                try:
+                    self._fine_ex = PeerExchange.from_process_group(self.fine.device, 1, 1, self.group)
+                    self._fine_ex.register_shards_distributed(self.fine, self.group)
+                except PeerExchangeUnavailable:
+                    self._fine_ex = False                 # every rank together: fall back to the all-reduce assembly
+            if self._fine_ex:
+                fine = self._fine_ex.score_rows(self.fine, queries, ids)
+            else:
+                fine = assemble_over_shards(self.fine.score_rows(queries, ids), self.group)
         else:
             fine = self.fine.score_rows(queries, ids)
             if self.coarse.world > 1:
