@@ -11,8 +11,8 @@ from ``torchrun`` (one process per GPU, ``sharded.ShardedSearcher``).
   ``k x (id, score)`` candidates into every peer's receive buffer — no waiting), then ONE
   ``crs_exchange_merge`` on the first device (waits for the pushes of this step and merges).  Everything is
   enqueued asynchronously; the only host synchronisation is the final copy of ``[nq, k]`` results;
-* ``fetch_rows`` / ``score_rows`` address rows by global id and are routed to the owning shard (the MMR
-  step reads the stored vectors of <= 2k survivors; no second collective).
+* ``fetch_rows`` addresses rows by global id and is routed to the owning shard (the MMR step reads the
+  stored vectors of <= 2k survivors; no second collective).
 
 The same device may appear several times (``devices=[0, 0]``): the shards then live side by side on one GPU,
 which is how the multi-device path is tested on a one-GPU box.
@@ -190,26 +190,6 @@ class MultiDeviceIndex:
             if sel.size:
                 out[sel] = sh.fetch_rows((local[sel] + sh.row_base).astype(np.uint32))
         return out
-
-    def score_rows(self, queries, ids):
-        """K8 on global ids (numpy): canonical score of every (query q, row ids[q, j]) pair."""
-        q = np.ascontiguousarray(queries, dtype=np.float32)
-        if q.ndim == 1:
-            q = q[None, :]
-        i = np.ascontiguousarray(ids, dtype=np.uint32)
-        if i.ndim == 1:
-            i = i[None, :]
-        shard, local = self._locate(np.where(i.reshape(-1) == 0xFFFFFFFF, -1, i.reshape(-1).astype(np.int64)))
-        shard, local = shard.reshape(i.shape), local.reshape(i.shape)
-        absent = np.iinfo(np.int32).min if self.is_int else -np.inf
-        res = np.full(i.shape, absent, dtype=np.int32 if self.is_int else np.float32)
-        for j, sh in enumerate(self.shards):
-            mine = shard == j
-            if mine.any():
-                lid = np.where(mine, local + sh.row_base, 0xFFFFFFFF).astype(np.uint32)
-                part = sh.score_rows(q, lid)
-                res[mine] = part[mine]
-        return res
 
     def mmr(self, vecs, relevance, lam: float, k_out: Optional[int] = None):
         return self.shards[0].mmr(vecs, relevance, lam, k_out)
