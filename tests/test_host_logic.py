@@ -70,3 +70,60 @@ def test_document_mask_equals_the_row_by_row_definition():
         assert np.array_equal(backend._doc_mask(docs, cond), want), cond
     with pytest.raises(ValueError):
         backend._doc_mask(docs, {"$like": "x"})
+
+
+def test_multi_device_id_routing_without_a_gpu():
+    """multi.MultiDeviceIndex keeps (first global id, n, shard, first local row) segments; global ids are insertion
+    indices.  The routing of ids and of a global allow-mask to the shards is plain numpy: checked here against a
+    brute-force table, on an instance whose shards are stand-ins."""
+    from compressed_rag_suite_b200.multi import MultiDeviceIndex
+
+    class FakeShard:
+        def __init__(self):
+            self.n = 0
+
+        def __len__(self):
+            return self.n
+
+    rng = np.random.default_rng(9)
+    g = 3
+    m = MultiDeviceIndex.__new__(MultiDeviceIndex)
+    m.shards = [FakeShard() for _ in range(g)]
+    m._seg, m._seg_start, m._count, m._next = [], [], 0, 0
+    owner, local = [], []
+    for n in [7, 1, 2, 50, 1, 1, 1, 13]:                      # the same dealing rule as MultiDeviceIndex.add
+        if n < g:
+            pieces = [(i, i + 1, (m._next + i) % g) for i in range(n)]
+            m._next = (m._next + n) % g
+        else:
+            per = (n + g - 1) // g
+            pieces = [(lo, min(lo + per, n), j) for j, lo in enumerate(range(0, n, per))]
+        for lo, hi, j in pieces:
+            sh = m.shards[j]
+            m._seg_start.append(m._count + lo)
+            m._seg.append((m._count + lo, hi - lo, j, sh.n))
+            for r in range(hi - lo):
+                owner.append(j)
+                local.append(sh.n + r)
+            sh.n += hi - lo
+        m._count += n
+    assert m._count == len(owner) == sum(len(s) for s in m.shards)
+    ids = rng.integers(0, m._count, 200)
+    sh, lo = m._locate(ids)
+    assert np.array_equal(sh, np.array(owner)[ids]) and np.array_equal(lo, np.array(local)[ids])
+    sh, lo = m._locate(np.array([-1, m._count, m._count + 5]))
+    assert (sh == -1).all()
+    allow = rng.random(m._count) < 0.4
+    per_shard = m._local_allow(allow)
+    for j in range(g):
+        want = np.zeros(len(m.shards[j]), dtype=bool)
+        for gid in range(m._count):
+            if owner[gid] == j:
+                want[local[gid]] = allow[gid]
+        assert np.array_equal(per_shard[j], want)
+    with pytest.raises(ValueError):
+        m._local_allow(np.ones(3, dtype=bool))
+    # every shard's ids grow with its local rows (ties inside a shard go to the lowest local row = first inserted)
+    for j in range(g):
+        gids = [gid for gid in range(m._count) if owner[gid] == j]
+        assert [local[gid] for gid in gids] == list(range(len(gids)))
