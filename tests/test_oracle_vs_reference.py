@@ -117,3 +117,51 @@ def test_vectorstore_contract_on_fake_chroma(ref):
     assert out["ids"] == [["chunk_0", "chunk_1", "chunk_2", "chunk_3"]]
     assert out["metadatas"][0][0] == {"page_number": 0, "tokens": 2}
     assert out["distances"][0] == sorted(out["distances"][0])
+
+
+def test_config1_golden_is_what_the_reference_ragpipeline_returns(ref, golden_dir):
+    """tests/golden/pipeline_c1_golden.json: re-run the reference's OWN RAGPipeline (index_documents on the 14 synthetic
+    pages, retrieve on the queries) with the stand-in embedder / tokenizer and compare with the committed file — the
+    chunks its chunker makes and the contexts it returns."""
+    import sys
+    import types
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import c1_standins as st
+    ri, rr, rc, fc = ref
+    fc.PRECISION = "f16"
+    import rag.chunking as ref_chunking
+    import rag.embedding as ref_embedding
+    import rag.pipeline as ref_pipeline
+    g = json.load(open(os.path.join(golden_dir, "pipeline_c1_golden.json")))
+    stored_of = {}
+
+    class PipelineEmbedder(st.HashSentenceTransformer):
+        def encode(self, texts, **kw):
+            out = super().encode(texts, **kw)
+            for i, t in enumerate([texts] if isinstance(texts, str) else list(texts)):
+                if t in stored_of:
+                    out[i] = stored_of[t]
+            return out
+
+    ref_embedding.SentenceTransformer = PipelineEmbedder
+    ref_chunking.nltk = types.SimpleNamespace(data=types.SimpleNamespace(load=lambda _p: st.RegexPunkt(), find=lambda _p: True),
+                                              download=lambda *a, **k: True)
+    cfg = json.loads(json.dumps(g["config"]))
+    cfg["vector_store"]["collection_name"] = f"c1_regen_{os.getpid()}"
+    pipe = ref_pipeline.RAGPipeline(cfg)
+    pipe.setup(model_interface=types.SimpleNamespace(model_type="instruct"))
+    pipe.index_documents(st.make_pages(g["n_pages"]), show_progress=False)
+    col = pipe.vector_store.collection
+    assert list(col._ids) == g["chunk_ids"] and list(col._docs) == g["chunk_texts"] and list(col._metas) == g["chunk_metas"]
+    x = np.stack(col._emb).astype(np.float32)
+    stored = encode.encode_rows(x, "f16", "cosine")[:, :x.shape[1]].astype(np.float32)
+    for t, v in zip(g["chunk_texts"], stored):
+        stored_of[t] = v
+    assert len(g["cases"]) >= 15
+    for case in g["cases"]:
+        got = pipe.retrieve(case["query"])
+        assert [c["chunk_id"] for c in got] == case["chunk_ids"]
+        assert [c["score"] for c in got] == case["scores"]
+        assert [c["distance"] for c in got] == case["distances"]
+        assert [c.get("rerank_score") for c in got] == case["rerank_scores"]
+        assert pipe.retriever.get_context_string(case["query"]) == case["context"]
